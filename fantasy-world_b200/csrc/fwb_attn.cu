@@ -1,0 +1,335 @@
+// fwb_attn.cu — non-causal flash attention forward on tcgen05 (sm_100a).
+//
+// Replaces:
+//   flash_attention()                  FantasyWorld/diffsynth_wan21/models/wan_video_dit.py:28-66   (DiT self / cross)
+//   F.scaled_dot_product_attention     FantasyWorld/fusion/layer/block.py:598-605                   (adapter, 2 directions)
+//   F.scaled_dot_product_attention     FantasyWorld/vggt/layers/attention.py:61                     (VGGT frame / global)
+//
+// One CTA = 256 query rows (two 128-row Q tiles, ping-pong) x one (batch, head); it streams all KV tiles of 128 keys.
+//   warps 0-3   softmax for Q tile 0 (thread r <-> query row r <-> TMEM lane r)
+//   warps 4-7   softmax for Q tile 1
+//   warp  8     MMA issuer (one elected thread): S_i = Q_i K_j^T (SS), O_i += P_i V_j (TS: P read from TMEM)
+//   warp  9     TMA producer: Q once, K/V rings (SWIZZLE_128B boxes of 64 columns)
+// TMEM (512 columns): S_0 | S_1 (fp32 128 cols each; P_i (bf16) overwrites the first 64 columns of S_i) | O_0 | O_1.
+// Softmax: fp32, exp2 with the scale folded in, lazy rescaling of O (only when the row max grows by > 2^8),
+// P rounded to bf16 before PV — the same rounding point as flash-attn / cuDNN SDPA.
+// head_dim 96 (adapter) runs on the D=128 instance: TMA zero-fills columns 96..127 and QK^T skips the dead K-steps.
+// Roofline: tensor-pipe bound, 4*B*H*Lq*Lk*D FLOP.
+#include <math.h>
+
+#include "../../include/fwb200.h"
+#include "fwb_common.cuh"
+#include "fwb_host.h"
+
+using namespace fwb;
+
+namespace {
+
+constexpr int kAttnThreads = 320;
+constexpr int BQ = 128;   // rows per Q tile
+constexpr int BKV = 128;  // keys per KV tile
+
+struct AttnParams {
+  __nv_bfloat16* out;
+  long long o_sb, o_sl, o_sh;
+  int Lq, Lk, d_real;
+  float scale_log2;
+};
+
+template <int D>
+struct AttnCfg {
+  static constexpr int kBoxes = D / 64;                   // 64-column TMA boxes per tile
+  static constexpr int kTileBytes = kBoxes * BQ * 128;    // Q / K / V tile bytes (128 rows)
+  static constexpr int kStages = (D == 128) ? 2 : 4;      // K ring depth == V ring depth
+  static constexpr int kSmemBytes = 2 * kTileBytes + 2 * kStages * kTileBytes + 1024;
+  static constexpr uint32_t kColS = 0;                    // S_i at columns i*128
+  static constexpr uint32_t kColO = 256;                  // O_i at columns 256 + i*D
+};
+
+template <int D>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using Cfg = AttnCfg<D>;
+  constexpr int ST = Cfg::kStages;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // [2][kTileBytes]
+  uint8_t* sK = smem + 2 * Cfg::kTileBytes;             // [ST][kTileBytes]
+  uint8_t* sV = sK + ST * Cfg::kTileBytes;              // [ST][kTileBytes]
+  __shared__ uint64_t q_full[2], k_full[ST], k_empty[ST], v_full[ST], v_empty[ST], s_full[2], p_full[2], o_full[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const uint32_t warp = warp_id_uniform();
+  const uint32_t lane = lane_id();
+  const int qblock = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
+  const int n_kv = (p.Lk + BKV - 1) / BKV;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);  // one arrive per softmax warp
+      mbar_init(&o_full[i], 1);
+    }
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 8) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 9) {
+    // ------------------------------------ TMA producer ------------------------------------
+    if (elect_one()) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_arrive_expect_tx(&q_full[i], Cfg::kTileBytes);
+        for (int b = 0; b < Cfg::kBoxes; ++b)
+          tma_load_4d(sQ + i * Cfg::kTileBytes + b * 16384, &tmQ, &q_full[i], b * 64, head, (qblock * 2 + i) * BQ,
+                      batch);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const uint32_t s = j % ST, ph = (j / ST) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], Cfg::kTileBytes);
+        for (int b = 0; b < Cfg::kBoxes; ++b)
+          tma_load_4d(sK + s * Cfg::kTileBytes + b * 16384, &tmK, &k_full[s], b * 64, head, j * BKV, batch);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], Cfg::kTileBytes);
+        for (int b = 0; b < Cfg::kBoxes; ++b)
+          tma_load_4d(sV + s * Cfg::kTileBytes + b * 16384, &tmV, &v_full[s], b * 64, head, j * BKV, batch);
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------ MMA issuer --------------------------------------
+    if (elect_one()) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);  // B = V is MN-major (d contiguous)
+      const int ksteps_qk = (p.d_real + 15) / 16;
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+
+      auto issue_qk = [&](int i, uint32_t ks) {
+        const uint32_t qa = q_addr + i * Cfg::kTileBytes, ka = k_addr + ks * Cfg::kTileBytes;
+        const uint32_t d_tmem = tmem_base + Cfg::kColS + i * 128;
+        for (int kk = 0; kk < ksteps_qk; ++kk) {
+          const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+          umma_ss(d_tmem, make_smem_desc(qa + off, 0, 1024, SWZ_128B), make_smem_desc(ka + off, 0, 1024, SWZ_128B),
+                  idesc_qk, kk > 0);
+        }
+      };
+      auto issue_pv = [&](int i, uint32_t vs, bool acc) {
+        const uint32_t va = v_addr + vs * Cfg::kTileBytes;
+        const uint32_t d_tmem = tmem_base + Cfg::kColO + i * D;
+        const uint32_t a_tmem = tmem_base + Cfg::kColS + i * 128;
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          // 16 kv rows per step = 2048 B; LBO = stride between the 64-column d boxes, SBO = 8 kv rows
+          umma_ts(d_tmem, a_tmem + kk * 8, make_smem_desc(va + kk * 2048, 16384, 1024, SWZ_128B), idesc_pv,
+                  acc || kk > 0);
+        }
+      };
+
+      mbar_wait(&q_full[0], 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      tc_commit(&s_full[0]);
+      mbar_wait(&q_full[1], 0);
+      tc_fence_after();
+      issue_qk(1, 0);
+      tc_commit(&s_full[1]);
+      tc_commit(&k_empty[0]);
+
+      for (int j = 0; j < n_kv; ++j) {
+        const uint32_t vs = j % ST, vph = (j / ST) & 1;
+        for (int i = 0; i < 2; ++i) {
+          mbar_wait(&p_full[i], j & 1);
+          if (i == 0) mbar_wait(&v_full[vs], vph);
+          tc_fence_after();
+          issue_pv(i, vs, j > 0);
+          if (i == 1) tc_commit(&v_empty[vs]);
+          if (j + 1 < n_kv) {
+            const uint32_t ks = (j + 1) % ST, kph = ((j + 1) / ST) & 1;
+            if (i == 0) {
+              mbar_wait(&k_full[ks], kph);
+              tc_fence_after();
+            }
+            issue_qk(i, ks);  // overwrites S_i/P_i: ordered after PV_i(j) by in-order MMA execution
+            tc_commit(&s_full[i]);
+            if (i == 1) tc_commit(&k_empty[ks]);
+          } else {
+            tc_commit(&o_full[i]);
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------ softmax + epilogue ------------------------------
+    const int i = warp >> 2;                 // Q tile handled by this warpgroup
+    const uint32_t quad = warp & 3;          // TMEM lane quadrant
+    const uint32_t lane_off = (quad * 32) << 16;
+    const uint32_t s_tmem = tmem_base + Cfg::kColS + i * 128 + lane_off;
+    const uint32_t o_tmem = tmem_base + Cfg::kColO + i * D + lane_off;
+    const float sl2 = p.scale_log2;
+    float m_used = -INFINITY;  // running (stale-tolerant) row max in scaled log2 units
+    float l_sum = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[i], j & 1);
+      tc_fence_after();
+      uint32_t v[128];
+      tmem_ld32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tmem_ld32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+      tmem_ld32(s_tmem + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
+      tmem_ld32(s_tmem + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
+      tmem_ld_wait();
+
+      if (j == n_kv - 1) {
+        const int valid = p.Lk - j * BKV;
+        if (valid < BKV) {
+#pragma unroll
+          for (int c = 0; c < 128; ++c)
+            if (c >= valid) v[c] = 0xFF800000u;  // -inf
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 128; c += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(v[c]));
+        mx1 = fmaxf(mx1, __uint_as_float(v[c + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(v[c + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(v[c + 3]));
+      }
+      const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
+      const bool need = m_new > m_used + 8.0f;
+      if (__any_sync(0xffffffffu, need)) {
+        const float m_next = fmaxf(m_used, m_new);
+        const float alpha = fast_exp2(m_used - m_next);  // m_used = -inf on the first tile -> 0
+        l_sum *= alpha;
+        m_used = m_next;
+        if (j > 0) {
+          // rescale this row of O.  PV_i(j-1) has completed: it was issued before S_i(j), whose commit we waited on.
+#pragma unroll
+          for (int c0 = 0; c0 < D; c0 += 16) {
+            uint32_t o[16];
+            tmem_ld16(o_tmem + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+            tmem_st16(o_tmem + c0, o);
+          }
+        }
+      }
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      uint32_t pk[64];
+#pragma unroll
+      for (int c = 0; c < 128; c += 4) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(v[c]), sl2, -m_used));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), sl2, -m_used));
+        const float p2 = fast_exp2(fmaf(__uint_as_float(v[c + 2]), sl2, -m_used));
+        const float p3 = fast_exp2(fmaf(__uint_as_float(v[c + 3]), sl2, -m_used));
+        a0 += p0; a1 += p1; a2 += p2; a3 += p3;
+        pk[c / 2] = pack_bf16x2(p0, p1);
+        pk[c / 2 + 1] = pack_bf16x2(p2, p3);
+      }
+      l_sum += (a0 + a1) + (a2 + a3);
+      tmem_st32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+      tmem_st32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[i]);
+    }
+
+    // epilogue: O / l  -> bf16 -> global
+    mbar_wait(&o_full[i], 0);
+    tc_fence_after();
+    const int row = (qblock * 2 + i) * BQ + quad * 32 + lane;
+    const float inv_l = 1.f / l_sum;
+    __nv_bfloat16* orow = p.out + (long long)batch * p.o_sb + (long long)row * p.o_sl + (long long)head * p.o_sh;
+#pragma unroll
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t o[32];
+      tmem_ld32(o_tmem + c0, o);
+      tmem_ld_wait();
+      if (row < p.Lq && c0 < p.d_real) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[c]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+          w.y = pack_bf16x2(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+          w.z = pack_bf16x2(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+          w.w = pack_bf16x2(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c0 + c) = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+int make_qkv_map(CUtensorMap* m, const fwb_tensor4_t* t, int B, int H, int L, int D) {
+  uint64_t dims[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)L, (uint64_t)B};
+  uint64_t str[3] = {(uint64_t)t->sh * 2, (uint64_t)t->sl * 2, (uint64_t)t->sb * 2};
+  uint32_t box[4] = {64, 1, 128, 1};
+  return make_tmap_bf16(m, t->ptr, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <int D>
+int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B, int H,
+                cudaStream_t stream) {
+  using Cfg = AttnCfg<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FWB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid((p.Lq + 2 * BQ - 1) / (2 * BQ), H, B);
+  attn_fwd_kernel<D><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  FWB_CUDA(cudaGetLastError());
+  return FWB_OK;
+}
+
+}  // namespace
+
+extern "C" int fwb_attn_fwd(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v,
+                            const fwb_tensor4_t* out, int B, int H, int Lq, int Lk, int D, float scale,
+                            cudaStream_t stream) {
+  FWB_CHECK(q && k && v && out && q->ptr && k->ptr && v->ptr && out->ptr, "attn: null pointer");
+  FWB_CHECK(D == 64 || D == 96 || D == 128, "attn: head_dim %d unsupported (64, 96, 128)", D);
+  FWB_CHECK(B > 0 && H > 0 && Lq > 0 && Lk > 0, "attn: empty problem B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk);
+  FWB_CHECK(H <= 65535 && B <= 65535, "attn: H and B must be <= 65535");
+  const fwb_tensor4_t* ts[4] = {q, k, v, out};
+  for (int i = 0; i < 4; ++i) {
+    FWB_CHECK(ts[i]->sb % 8 == 0 && ts[i]->sl % 8 == 0 && ts[i]->sh % 8 == 0, "attn: strides must be multiples of 8 elements");
+    FWB_CHECK((reinterpret_cast<uintptr_t>(ts[i]->ptr) & 15) == 0, "attn: pointers must be 16-byte aligned");
+  }
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_qkv_map(&tq, q, B, H, Lq, D))) return rc;
+  if ((rc = make_qkv_map(&tk, k, B, H, Lk, D))) return rc;
+  if ((rc = make_qkv_map(&tv, v, B, H, Lk, D))) return rc;
+  AttnParams p;
+  p.out = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(out->ptr));
+  p.o_sb = out->sb; p.o_sl = out->sl; p.o_sh = out->sh;
+  p.Lq = Lq; p.Lk = Lk; p.d_real = D;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  if (D == 64) return launch_attn<64>(tq, tk, tv, p, B, H, stream);
+  return launch_attn<128>(tq, tk, tv, p, B, H, stream);
+}

@@ -1,0 +1,123 @@
+"""Thin torch-tensor wrappers over the C ABI (include/fwb200.h).  Device pointers + sizes only cross the boundary."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from ._lib import Epilogue, Tensor4, check, lib
+
+ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_RELU, ACT_SILU = 0, 1, 2, 3, 4
+ROUND_AFTER_BIAS, ROUND_AFTER_ACT, ROUND_AFTER_AFFINE, ROUND_AFTER_SCALE2 = 1, 2, 4, 8
+DT_BF16, DT_F32 = 0, 1
+
+__all__ = [
+    "ACT_NONE", "ACT_GELU_TANH", "ACT_GELU_ERF", "ACT_RELU", "ACT_SILU",
+    "ROUND_AFTER_BIAS", "ROUND_AFTER_ACT", "ROUND_AFTER_AFFINE", "ROUND_AFTER_SCALE2",
+    "device_ok", "require_device", "linear", "attention", "bringup_mma",
+]
+
+
+def device_ok() -> bool:
+    return bool(lib.fwb_device_ok())
+
+
+def require_device():
+    if not device_ok():
+        msg = lib.fwb_last_error()
+        raise RuntimeError("fwb200 needs a B200 (sm_100) device: " + (msg.decode() if msg else ""))
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t: torch.dtype) -> int:
+    if t == torch.bfloat16:
+        return DT_BF16
+    if t == torch.float32:
+        return DT_F32
+    raise TypeError(f"unsupported dtype {t}")
+
+
+def _f32vec(v, n, name):
+    if v is None:
+        return None
+    if not (v.is_cuda and v.dtype == torch.float32 and v.is_contiguous() and v.numel() == n):
+        raise ValueError(f"{name} must be a contiguous fp32 CUDA vector of {n} elements")
+    return v
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = ACT_NONE, scale1=None, shift1=None, scale2=None,
+           resid=None, out=None, out_dtype=torch.bfloat16, round_flags: int = 0) -> torch.Tensor:
+    """out = resid + scale2 * (scale1 * act(x @ w.T + bias) + shift1); x [..., K] bf16, w [N, K] bf16."""
+    if not (x.is_cuda and w.is_cuda):
+        raise RuntimeError("fwb200.linear: CUDA tensors required (no CPU fallback)")
+    if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
+        raise TypeError("fwb200.linear: x and w must be bf16")
+    K = x.shape[-1]
+    N = w.shape[0]
+    assert w.shape[1] == K and w.stride(1) == 1
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=out_dtype)
+    out2 = out.view(-1, N) if out.dim() != 2 else out
+    assert out2.shape == (M, N) and out2.stride(1) == 1
+    ep = Epilogue()
+    bias = _f32vec(bias, N, "bias")
+    scale1 = _f32vec(scale1, N, "scale1")
+    shift1 = _f32vec(shift1, N, "shift1")
+    scale2 = _f32vec(scale2, N, "scale2")
+    ep.bias = bias.data_ptr() if bias is not None else None
+    ep.scale1 = scale1.data_ptr() if scale1 is not None else None
+    ep.shift1 = shift1.data_ptr() if shift1 is not None else None
+    ep.scale2 = scale2.data_ptr() if scale2 is not None else None
+    if resid is not None:
+        r2 = resid.reshape(-1, N)
+        assert r2.shape == (M, N) and r2.stride(1) == 1
+        ep.resid, ep.resid_ld, ep.resid_dtype = r2.data_ptr(), r2.stride(0), _dt(r2.dtype)
+    else:
+        ep.resid, ep.resid_ld, ep.resid_dtype = None, 0, 0
+    ep.out, ep.out_ld, ep.out_dtype = out2.data_ptr(), out2.stride(0), _dt(out2.dtype)
+    ep.act, ep.round_flags = act, round_flags
+    check(lib.fwb_gemm_bf16(x2.data_ptr(), x2.stride(0), w.data_ptr(), w.stride(0), M, N, K, C.byref(ep), _stream()),
+          "fwb_gemm_bf16")
+    return out.view(*x.shape[:-1], N) if out.dim() == 2 and x.dim() != 2 else out
+
+
+def _t4(t: torch.Tensor) -> Tensor4:
+    # t: [B, L, H, D] view with unit stride on D
+    assert t.dim() == 4 and t.stride(3) == 1 and t.dtype == torch.bfloat16 and t.is_cuda
+    r = Tensor4()
+    r.ptr, r.sb, r.sl, r.sh = t.data_ptr(), t.stride(0), t.stride(1), t.stride(2)
+    return r
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float | None = None, out=None) -> torch.Tensor:
+    """softmax(scale * q k^T) v, non-causal. q [B, Lq, H, D], k/v [B, Lk, H, D] (bf16 views, D contiguous)."""
+    B, Lq, H, D = q.shape
+    Lk = k.shape[1]
+    assert k.shape == (B, Lk, H, D) and v.shape == (B, Lk, H, D)
+    if scale is None:
+        scale = 1.0 / math.sqrt(D)
+    if out is None:
+        out = torch.empty((B, Lq, H, D), device=q.device, dtype=torch.bfloat16)
+    tq, tk, tv, to = _t4(q), _t4(k), _t4(v), _t4(out)
+    check(lib.fwb_attn_fwd(C.byref(tq), C.byref(tk), C.byref(tv), C.byref(to), B, H, Lq, Lk, D, float(scale), _stream()),
+          "fwb_attn_fwd")
+    return out
+
+
+def bringup_mma(A: torch.Tensor, Bm: torch.Tensor, N: int, K: int, a_in_tmem: bool, b_mn_major: bool, overrides=None):
+    D = torch.empty((128, N), device=A.device, dtype=torch.float32)
+    ov = None
+    if overrides is not None:
+        arr = (C.c_uint32 * 8)(*[0xFFFFFFFF if o is None else int(o) for o in overrides])
+        ov = C.cast(arr, C.c_void_p)
+    check(lib.fwb_bringup_mma(A.data_ptr(), Bm.data_ptr(), D.data_ptr(), N, K, int(a_in_tmem), int(b_mn_major), ov,
+                              _stream()), "fwb_bringup_mma")
+    return D

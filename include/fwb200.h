@@ -1,0 +1,92 @@
+/* fwb200.h — C ABI of libfwb200.so, the B200 (sm_100a) kernel library behind the FantasyWorld denoising hot path.
+ *
+ * The reference (Fantasy-AMAP/fantasy-world) has no native code and no FFI: its "operator API" for this path is the
+ * set of PyTorch library calls listed in SURVEY.md §2.1 (K1..K11).  Each entry point below replaces one family of those
+ * call sites; the file:line it replaces is cited per function.  The host side (Python, package
+ * `fantasy-world_b200/FantasyWorld`) mirrors the reference's nn.Module surface and calls these through ctypes.
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is a DEVICE pointer unless stated; no torch types
+ *   - the caller owns all memory (outputs are pre-allocated); kernels never allocate
+ *   - all launches go to `stream` (a cudaStream_t); no host synchronisation inside
+ *   - return value: 0 = ok, non-zero = error; `fwb_last_error()` returns a thread-local message
+ *   - bf16 tensors are row-major with the stated leading dimensions (in ELEMENTS)
+ */
+#ifndef FWB200_H_
+#define FWB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FWB_ABI_VERSION 1
+
+typedef struct CUstream_st* fwb_stream_t; /* == cudaStream_t */
+
+enum { FWB_DT_BF16 = 0, FWB_DT_F32 = 1 };
+enum { FWB_ACT_NONE = 0, FWB_ACT_GELU_TANH = 1, FWB_ACT_GELU_ERF = 2, FWB_ACT_RELU = 3, FWB_ACT_SILU = 4 };
+
+/* bits of fwb_epilogue_t.round_flags: round the running value to bf16 (as CUDA autocast does between ops) */
+enum {
+  FWB_ROUND_AFTER_BIAS = 1,   /* nn.Linear output is bf16 under autocast */
+  FWB_ROUND_AFTER_ACT = 2,    /* activation output bf16 */
+  FWB_ROUND_AFTER_AFFINE = 4, /* after *scale1 + shift1 */
+  FWB_ROUND_AFTER_SCALE2 = 8
+};
+
+/* ---- introspection ------------------------------------------------------------------------------------------- */
+const char* fwb_last_error(void);
+int fwb_abi_version(void);
+/* 1 if a sm_100 device is current, else 0 (and fwb_last_error() says why). Product paths refuse to run without it. */
+int fwb_device_ok(void);
+
+/* ---- K6/K10: Linear (+bias, activation, column affine, gate, residual) -------------------------------------------
+ * out[m,n] = resid[m,n] + scale2[n] * ( scale1[n] * act( sum_k A[m,k] W[n,k] + bias[n] ) + shift1[n] )
+ * Replaces: nn.Linear call sites wan_video_dit.py:166-169,216-225,274-275 ; GateModule wan_video_dit.py:246-251 ;
+ *           fusion/layer/block.py:340-346,218-219 ; vggt/layers/attention.py:42,46 ; vggt/layers/mlp.py:29-31 ;
+ *           vggt/layers/block.py:73-81 (LayerScale / post-MLP modulation) ; camera_control.py:27-51 ; vggt.py:32.
+ * A: [M,K] bf16 (lda), W: [N,K] bf16 (ldw) — nn.Linear weight layout.  K, lda, ldw, N, out_ld, resid_ld % 8 == 0.
+ * All column vectors are fp32 [N] (NULL = absent).  Accumulation fp32 on tcgen05 tensor cores. */
+typedef struct {
+  const float* bias;
+  const float* scale1;
+  const float* shift1;
+  const float* scale2;
+  const void* resid; /* [M,N] or NULL */
+  int64_t resid_ld;
+  int resid_dtype; /* FWB_DT_* */
+  void* out;       /* [M,N] */
+  int64_t out_ld;
+  int out_dtype; /* FWB_DT_* */
+  int act;       /* FWB_ACT_* */
+  int round_flags;
+} fwb_epilogue_t;
+
+int fwb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, const fwb_epilogue_t* ep,
+                  fwb_stream_t stream);
+
+/* ---- K1..K5: non-causal softmax attention ------------------------------------------------------------------------
+ * out[b,l,h,:] = softmax_j( scale * q[b,l,h,:] . k[b,j,h,:] ) v[b,j,h,:]      (no mask, no dropout)
+ * Replaces: flash_attention() wan_video_dit.py:28-66 (DiT self/cross attention), F.scaled_dot_product_attention at
+ *           fusion/layer/block.py:598-605 (adapter, both directions) and vggt/layers/attention.py:61 (frame/global).
+ * q,k,v,out: bf16, head_dim D in {64, 96, 128} contiguous; element strides given per tensor for batch (sb),
+ * token (sl) and head (sh); all strides % 8 == 0.  scale is the softmax scale (reference: 1/sqrt(D)).
+ * fp32 softmax statistics, P rounded to bf16 before PV (as flash-attn / cuDNN do), fp32 accumulation. */
+typedef struct {
+  const void* ptr;
+  int64_t sb, sl, sh;
+} fwb_tensor4_t;
+
+int fwb_attn_fwd(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v, const fwb_tensor4_t* out, int B,
+                 int H, int Lq, int Lk, int D, float scale, fwb_stream_t stream);
+
+/* ---- bring-up micro-test (tests only; pins tcgen05 descriptor encodings on hardware) ------------------------------ */
+int fwb_bringup_mma(const void* A, const void* B, float* D, int N, int K, int a_in_tmem, int b_mn_major,
+                    const uint32_t* overrides, fwb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FWB200_H_ */
