@@ -34,6 +34,7 @@ struct AttnParams {
   long long o_sb, o_sl, o_sh;
   int Lq, Lk, d_real;
   float scale_log2;
+  int accumulate;  // out = bf16(out + bf16(result))  (sum of two attentions sharing q: wan_video_dit.py:197-200)
 };
 
 template <int D>
@@ -268,11 +269,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (row < p.Lq && c0 < p.d_real) {
 #pragma unroll
         for (int c = 0; c < 32; c += 8) {
+          float y[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) y[t] = __uint_as_float(o[c + t]) * inv_l;
+          if (p.accumulate) {
+            const uint4 prev = *reinterpret_cast<const uint4*>(orow + c0 + c);
+            const uint32_t pw[4] = {prev.x, prev.y, prev.z, prev.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              y[2 * t] = bf16_round(y[2 * t]) + __uint_as_float(pw[t] << 16);
+              y[2 * t + 1] = bf16_round(y[2 * t + 1]) + __uint_as_float(pw[t] & 0xFFFF0000u);
+            }
+          }
           uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(o[c]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
-          w.y = pack_bf16x2(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
-          w.z = pack_bf16x2(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
-          w.w = pack_bf16x2(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+          w.x = pack_bf16x2(y[0], y[1]);
+          w.y = pack_bf16x2(y[2], y[3]);
+          w.z = pack_bf16x2(y[4], y[5]);
+          w.w = pack_bf16x2(y[6], y[7]);
           *reinterpret_cast<uint4*>(orow + c0 + c) = w;
         }
       }
@@ -310,7 +323,7 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
 
 extern "C" int fwb_attn_fwd(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v,
                             const fwb_tensor4_t* out, int B, int H, int Lq, int Lk, int D, float scale,
-                            cudaStream_t stream) {
+                            int accumulate, cudaStream_t stream) {
   FWB_CHECK(q && k && v && out && q->ptr && k->ptr && v->ptr && out->ptr, "attn: null pointer");
   FWB_CHECK(D == 64 || D == 96 || D == 128, "attn: head_dim %d unsupported (64, 96, 128)", D);
   FWB_CHECK(B > 0 && H > 0 && Lq > 0 && Lk > 0, "attn: empty problem B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk);
@@ -330,6 +343,7 @@ extern "C" int fwb_attn_fwd(const fwb_tensor4_t* q, const fwb_tensor4_t* k, cons
   p.o_sb = out->sb; p.o_sl = out->sl; p.o_sh = out->sh;
   p.Lq = Lq; p.Lk = Lk; p.d_real = D;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.accumulate = accumulate;
   if (D == 64) return launch_attn<64>(tq, tk, tv, p, B, H, stream);
   return launch_attn<128>(tq, tk, tv, p, B, H, stream);
 }

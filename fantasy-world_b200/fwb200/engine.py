@@ -1,0 +1,256 @@
+"""engine.py — the fused execution of the hot-path blocks on top of the C-ABI kernels.
+
+The nn.Module classes under fantasy-world_b200/FantasyWorld/ (same names, signatures and state_dict keys as the
+reference) own the parameters; their forward() bodies delegate here.  Everything below launches only fwb200 kernels
+for the token-sized work; torch is used for allocation and for O(C)-sized vector prep (modulation vectors, tables).
+
+Rounding points follow the reference's CUDA-autocast run — see oracle/fw_oracle.py, which
+restates the same points on the CPU.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .ops import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_RELU, ACT_SILU, ROUND_AFTER_ACT, ROUND_AFTER_AFFINE, ROUND_AFTER_BIAS)
+
+BF16 = torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# derived-tensor cache (fp32 copies of bias / norm vectors, padded or concatenated weights)
+# ------------------------------------------------------------------------------------------------------------------
+def derived(owner, name, fn, *srcs):
+    """Cache fn(*srcs) on `owner` (an nn.Module); recomputed when a source tensor is replaced or modified."""
+    cache = owner.__dict__.setdefault("_fwb_cache", {})
+    key = tuple((s.data_ptr(), s._version, s.device, s.dtype) for s in srcs)
+    hit = cache.get(name)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    with torch.no_grad():
+        val = fn(*srcs)
+    cache[name] = (key, val)
+    return val
+
+
+def f32(owner, name, t):
+    return derived(owner, "f32:" + name, lambda s: s.detach().float().contiguous().view(-1), t)
+
+
+def w16(owner, name, t):
+    """bf16 contiguous [N, K] view of a Linear / 1x1 conv weight."""
+    return derived(owner, "w16:" + name, lambda s: s.detach().to(BF16).reshape(s.shape[0], -1).contiguous(), t)
+
+
+def lin(x, layer, *, tag="", **kw):
+    """fwb200.linear on an nn.Linear's parameters (bias as cached fp32)."""
+    w = w16(layer, tag + "w", layer.weight)
+    b = f32(layer, tag + "b", layer.bias) if layer.bias is not None else None
+    return ops.linear(x, w, bias=b, **kw)
+
+
+def as_bf16(x):
+    return x if x.dtype == BF16 else x.to(BF16)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# RoPE tables
+# ------------------------------------------------------------------------------------------------------------------
+_table_cache: dict = {}
+
+
+def complex_to_cos_sin(freqs: torch.Tensor, device) -> torch.Tensor:
+    """complex [L, 1, hd/2] (reference layout) -> fp32 [L, hd/2, 2] (cos, sin) on `device`; cached by identity."""
+    key = ("cs", freqs.data_ptr(), freqs._version, tuple(freqs.shape), str(device))
+    hit = _table_cache.get(key)
+    if hit is None:
+        f = freqs.reshape(freqs.shape[0], -1)
+        hit = torch.stack([f.real, f.imag], dim=-1).to(torch.float32).contiguous().to(device)
+        if len(_table_cache) > 64:
+            _table_cache.clear()
+        _table_cache[key] = hit
+    return hit
+
+
+def rope2d_expanded(pos: torch.Tensor, base: float = 100.0):
+    """VGGT 2-D RoPE tables expanded per token: pos int [rows, 2] -> (cos, sin) fp32 [rows, 64].
+    Same arithmetic as vggt/layers/rope.py:82-110,153-167 (fp32 angles, integer gather)."""
+    key = ("r2d", pos.data_ptr(), pos._version, tuple(pos.shape), base)
+    hit = _table_cache.get(key)
+    if hit is None:
+        p = pos.reshape(-1, 2).long()
+        dim = 32
+        exponents = torch.arange(0, dim, 2, device=p.device).float() / dim
+        inv_freq = 1.0 / (base ** exponents)
+        max_pos = int(p.max()) + 1
+        ang = torch.einsum("i,j->ij", torch.arange(max_pos, device=p.device, dtype=inv_freq.dtype), inv_freq)
+        ang = torch.cat((ang, ang), dim=-1)
+        cos_t, sin_t = ang.cos(), ang.sin()
+        cosT = torch.cat([cos_t[p[:, 0]], cos_t[p[:, 1]]], dim=-1).contiguous()
+        sinT = torch.cat([sin_t[p[:, 0]], sin_t[p[:, 1]]], dim=-1).contiguous()
+        hit = (cosT, sinT)
+        if len(_table_cache) > 64:
+            _table_cache.clear()
+        _table_cache[key] = hit
+    return hit
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# DiT block pieces (reference: diffsynth_wan21/models/wan_video_dit.py DiTBlock / SelfAttention / CrossAttention)
+# ------------------------------------------------------------------------------------------------------------------
+def dit_mod_vectors(block, t_mod):
+    """(modulation + t_mod).chunk(6) as fp32 vectors: shift, (1+scale) [rounded to bf16 first], gate — twice."""
+    m = (block.modulation.to(BF16) + t_mod.to(BF16))  # [1, 6, C] bf16 add, as under autocast
+    assert m.shape[0] == 1, "fused path handles batch 1 (the reference sampler's batch)"
+    one_plus = (1 + m[0, [1, 4]]).float()              # bf16(1 + scale)
+    mf = m[0].float()
+    return dict(shift_msa=mf[0].contiguous(), mul_msa=one_plus[0].contiguous(), gate_msa=mf[2].contiguous(),
+                shift_mlp=mf[3].contiguous(), mul_mlp=one_plus[1].contiguous(), gate_mlp=mf[5].contiguous())
+
+
+def dit_self_attn(sa, h, cos_sin, x_resid, gate):
+    """x_resid + gate * o(attn(rope(norm_q(q(h))), rope(norm_k(k(h))), v(h)))  — wan_video_dit.py:175-182, 301."""
+    L = h.shape[0]
+    H, D = sa.num_heads, sa.head_dim
+    q = lin(h, sa.q)
+    k = lin(h, sa.k)
+    v = lin(h, sa.v)
+    ops.rmsnorm_rope_(q, w=f32(sa.norm_q, "w", sa.norm_q.weight), eps=sa.norm_q.eps, cos_sin=cos_sin, head_dim=D)
+    ops.rmsnorm_rope_(k, w=f32(sa.norm_k, "w", sa.norm_k.weight), eps=sa.norm_k.eps, cos_sin=cos_sin, head_dim=D)
+    o = ops.attention(q.view(1, L, H, D), k.view(1, L, H, D), v.view(1, L, H, D))
+    return lin(o.view(L, H * D), sa.o, scale1=gate, resid=x_resid, round_flags=ROUND_AFTER_BIAS | ROUND_AFTER_AFFINE)
+
+
+def cross_kv(ca, context):
+    """Loop-invariant K/V of the text / CLIP context — cached per context tensor."""
+    cache = ca.__dict__.setdefault("_fwb_kv", {})
+    key = (context.data_ptr(), context._version, tuple(context.shape))
+    hit = cache.get(key)
+    if hit is None:
+        ctx = as_bf16(context)
+        assert ctx.shape[0] == 1
+        H, D = ca.num_heads, ca.head_dim
+        if ca.has_image_input:
+            img, txt = ctx[0, :257], ctx[0, 257:]
+        else:
+            img, txt = None, ctx[0]
+        k = lin(txt.contiguous(), ca.k)
+        ops.rmsnorm_rope_(k, w=f32(ca.norm_k, "w", ca.norm_k.weight), eps=ca.norm_k.eps)
+        v = lin(txt.contiguous(), ca.v)
+        hit = [k.view(1, -1, H, D), v.view(1, -1, H, D), None, None]
+        if img is not None:
+            ki = lin(img.contiguous(), ca.k_img)
+            ops.rmsnorm_rope_(ki, w=f32(ca.norm_k_img, "w", ca.norm_k_img.weight), eps=ca.norm_k_img.eps)
+            vi = lin(img.contiguous(), ca.v_img)
+            hit[2], hit[3] = ki.view(1, -1, H, D), vi.view(1, -1, H, D)
+        if len(cache) >= 4:
+            cache.clear()
+        cache[key] = hit
+    return hit
+
+
+def dit_cross_attn_core(ca, n3, context):
+    """q-projection + text attention (+ CLIP attention, summed in bf16) — wan_video_dit.py:185-201.  Returns [L, C]."""
+    L = n3.shape[0]
+    H, D = ca.num_heads, ca.head_dim
+    k, v, ki, vi = cross_kv(ca, context)
+    q = lin(n3, ca.q)
+    ops.rmsnorm_rope_(q, w=f32(ca.norm_q, "w", ca.norm_q.weight), eps=ca.norm_q.eps)
+    q4 = q.view(1, L, H, D)
+    o = ops.attention(q4, k, v)
+    if ki is not None:
+        ops.attention(q4, ki, vi, out=o, accumulate=True)
+    return o.view(L, H * D)
+
+
+def dit_ffn(block, x, mods):
+    """x + gate_mlp * ffn(modulate(norm2(x)))  — wan_video_dit.py:288-294."""
+    h = ops.ln_modulate(x, eps=block.norm2.eps, mul=mods["mul_mlp"], add=mods["shift_mlp"])
+    h = lin(h, block.ffn[0], act=ACT_GELU_TANH, round_flags=ROUND_AFTER_BIAS | ROUND_AFTER_ACT)
+    return lin(h, block.ffn[2], scale1=mods["gate_mlp"], resid=x, round_flags=ROUND_AFTER_BIAS | ROUND_AFTER_AFFINE)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# VGGT block pieces (reference: vggt/layers/block.py Block, vggt/layers/attention.py Attention)
+# ------------------------------------------------------------------------------------------------------------------
+def vggt_mod_vectors(block, e0):
+    """(modulation + e0).chunk(6) in fp32 — vggt/layers/block.py:95-104 (batch 1)."""
+    assert e0 is not None and e0.shape[0] == 1
+    e = (block.modulation.float() + e0.float())[0]  # [6, C]
+    return dict(add1=e[0].contiguous(), mul1=(1 + e[1]).contiguous(), add2=e[3].contiguous(),
+                mul2=(1 + e[4]).contiguous(), e5=e[5].contiguous())
+
+
+def vggt_attn_part(block, x, tables, mods, n_batch):
+    """x + ls1(proj(attn(norm1(x)*(1+e1)+e0)))  with x [rows, C] (rows = n_batch * tokens) — block.py:73-76."""
+    rows, C = x.shape
+    at = block.attn
+    H = at.num_heads
+    mul = mods["mul1"] if mods is not None else None
+    add = mods["add1"] if mods is not None else None
+    h = ops.ln_modulate(x, eps=block.norm1.eps, w=f32(block.norm1, "w", block.norm1.weight),
+                        b=f32(block.norm1, "b", block.norm1.bias), mul=mul, add=add)
+    qkv = lin(h, at.qkv)
+    cosT, sinT = tables
+    ops.ln64_rope2d_(qkv, H, eps=at.q_norm.eps, qw=f32(at.q_norm, "w", at.q_norm.weight),
+                     qb=f32(at.q_norm, "b", at.q_norm.bias), kw=f32(at.k_norm, "w", at.k_norm.weight),
+                     kb=f32(at.k_norm, "b", at.k_norm.bias), cosT=cosT, sinT=sinT)
+    q5 = qkv.view(n_batch, rows // n_batch, 3, H, C // H)
+    o = ops.attention(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2])
+    gamma = f32(block.ls1, "g", block.ls1.gamma)
+    return lin(o.view(rows, C), at.proj, scale1=gamma, resid=x, out_dtype=x.dtype,
+               round_flags=ROUND_AFTER_BIAS | ROUND_AFTER_AFFINE)
+
+
+def vggt_ffn_part(block, x, mods):
+    """x + ls2(mlp(norm2(x)) * (1+e4) + e3) * e5  (modulation AFTER the MLP; fp32 stream) — block.py:78-81."""
+    h = ops.ln_modulate(x, eps=block.norm2.eps, w=f32(block.norm2, "w", block.norm2.weight),
+                        b=f32(block.norm2, "b", block.norm2.bias))
+    h = lin(h, block.mlp.fc1, act=ACT_GELU_ERF, round_flags=ROUND_AFTER_BIAS | ROUND_AFTER_ACT)
+    gamma = f32(block.ls2, "g", block.ls2.gamma)
+    if mods is None:
+        return lin(h, block.mlp.fc2, scale1=gamma, resid=x, out_dtype=x.dtype,
+                   round_flags=ROUND_AFTER_BIAS | ROUND_AFTER_AFFINE)
+    return lin(h, block.mlp.fc2, scale1=mods["mul2"], shift1=mods["add2"], scale2=gamma * mods["e5"], resid=x,
+               out_dtype=torch.float32, round_flags=ROUND_AFTER_BIAS)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# bidirectional adapter (reference: fusion/layer/block.py CrossModalityBiAttentionBlock / BiMultiHeadAttention)
+# ------------------------------------------------------------------------------------------------------------------
+def bicross(blk, x1, x2, cs_dit, cs_agg):
+    """x1 [L1, C1] bf16 (video), x2 [L2, C2] fp32|bf16 (geometry) -> updated (x1, x2)."""
+    ca = blk.cross_attn
+    H, D, E = ca.num_heads, ca.head_dim, ca.embed_dim
+    L1, L2 = x1.shape[0], x2.shape[0]
+    n1 = ops.ln_modulate(x1, eps=blk.attn_norm_m1.eps)
+    n2 = ops.ln_modulate(x2, eps=blk.attn_norm_m2.eps)
+    # one GEMM per stream: [q | v1] and [k | v2]
+    w1 = derived(ca, "w_qv1", lambda a, b: torch.cat([a, b], 0).to(BF16).contiguous(), ca.m1_proj.weight, ca.values_m1_proj.weight)
+    b1 = derived(ca, "b_qv1", lambda a, b: torch.cat([a, b], 0).float().contiguous(), ca.m1_proj.bias, ca.values_m1_proj.bias)
+    w2 = derived(ca, "w_kv2", lambda a, b: torch.cat([a, b], 0).to(BF16).contiguous(), ca.m2_proj.weight, ca.values_m2_proj.weight)
+    b2 = derived(ca, "b_kv2", lambda a, b: torch.cat([a, b], 0).float().contiguous(), ca.m2_proj.bias, ca.values_m2_proj.bias)
+    qv1 = ops.linear(n1, w1, bias=b1)
+    kv2 = ops.linear(n2, w2, bias=b2)
+    ops.rmsnorm_rope_(qv1[:, :E], cos_sin=cs_dit, head_dim=D)
+    ops.rmsnorm_rope_(kv2[:, :E], cos_sin=cs_agg, head_dim=D)
+    q = qv1[:, :E].unflatten(1, (H, D)).unsqueeze(0)
+    v1 = qv1[:, E:].unflatten(1, (H, D)).unsqueeze(0)
+    k = kv2[:, :E].unflatten(1, (H, D)).unsqueeze(0)
+    v2 = kv2[:, E:].unflatten(1, (H, D)).unsqueeze(0)
+    o1 = ops.attention(q, k, v2)   # video <- geometry
+    o2 = ops.attention(k, q, v1)   # geometry <- video
+    rf = ROUND_AFTER_BIAS | ROUND_AFTER_AFFINE
+    x1 = lin(o1.view(L1, E), ca.out_m1_proj, scale1=f32(blk, "g1", blk.gamma_m1), resid=x1, round_flags=rf)
+    x2 = lin(o2.view(L2, E), ca.out_m2_proj, scale1=f32(blk, "g2", blk.gamma_m2), resid=x2, out_dtype=x2.dtype,
+             round_flags=rf)
+    return x1, x2
+
+
+# small MLPs on a handful of rows (time embeddings etc.)
+def mlp_silu(x, l0, l2):
+    h = lin(as_bf16(x), l0, act=ACT_SILU, round_flags=ROUND_AFTER_BIAS | ROUND_AFTER_ACT)
+    return lin(h, l2, round_flags=ROUND_AFTER_BIAS)
+
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -16,7 +16,25 @@ __all__ = [
     "ACT_NONE", "ACT_GELU_TANH", "ACT_GELU_ERF", "ACT_RELU", "ACT_SILU",
     "ROUND_AFTER_BIAS", "ROUND_AFTER_ACT", "ROUND_AFTER_AFFINE", "ROUND_AFTER_SCALE2",
     "device_ok", "require_device", "linear", "attention", "bringup_mma",
+    "ln_modulate", "rmsnorm_rope_", "ln64_rope2d_", "cfg_euler_step_", "launch_count", "reset_launch_count",
 ]
+
+_LAUNCHES = 0
+
+
+def launch_count() -> int:
+    """Number of fwb200 kernel launches issued through this binding since the last reset."""
+    return _LAUNCHES
+
+
+def reset_launch_count():
+    global _LAUNCHES
+    _LAUNCHES = 0
+
+
+def _count(n=1):
+    global _LAUNCHES
+    _LAUNCHES += n
 
 
 def device_ok() -> bool:
@@ -84,6 +102,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = ACT_NONE, 
         ep.resid, ep.resid_ld, ep.resid_dtype = None, 0, 0
     ep.out, ep.out_ld, ep.out_dtype = out2.data_ptr(), out2.stride(0), _dt(out2.dtype)
     ep.act, ep.round_flags = act, round_flags
+    _count()
     check(lib.fwb_gemm_bf16(x2.data_ptr(), x2.stride(0), w.data_ptr(), w.stride(0), M, N, K, C.byref(ep), _stream()),
           "fwb_gemm_bf16")
     return out.view(*x.shape[:-1], N) if out.dim() == 2 and x.dim() != 2 else out
@@ -97,7 +116,8 @@ def _t4(t: torch.Tensor) -> Tensor4:
     return r
 
 
-def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float | None = None, out=None) -> torch.Tensor:
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float | None = None, out=None,
+              accumulate: bool = False) -> torch.Tensor:
     """softmax(scale * q k^T) v, non-causal. q [B, Lq, H, D], k/v [B, Lk, H, D] (bf16 views, D contiguous)."""
     B, Lq, H, D = q.shape
     Lk = k.shape[1]
@@ -107,8 +127,9 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
     if out is None:
         out = torch.empty((B, Lq, H, D), device=q.device, dtype=torch.bfloat16)
     tq, tk, tv, to = _t4(q), _t4(k), _t4(v), _t4(out)
-    check(lib.fwb_attn_fwd(C.byref(tq), C.byref(tk), C.byref(tv), C.byref(to), B, H, Lq, Lk, D, float(scale), _stream()),
-          "fwb_attn_fwd")
+    _count()
+    check(lib.fwb_attn_fwd(C.byref(tq), C.byref(tk), C.byref(tv), C.byref(to), B, H, Lq, Lk, D, float(scale), int(accumulate),
+                           _stream()), "fwb_attn_fwd")
     return out
 
 
@@ -121,3 +142,60 @@ def bringup_mma(A: torch.Tensor, Bm: torch.Tensor, N: int, K: int, a_in_tmem: bo
     check(lib.fwb_bringup_mma(A.data_ptr(), Bm.data_ptr(), D.data_ptr(), N, K, int(a_in_tmem), int(b_mn_major), ov,
                               _stream()), "fwb_bringup_mma")
     return D
+
+
+def _vec(v, n, name):
+    return None if v is None else _f32vec(v, n, name).data_ptr()
+
+
+def ln_modulate(x: torch.Tensor, *, eps: float, w=None, b=None, mul=None, add=None, out=None) -> torch.Tensor:
+    """out = bf16((LN(x) * w + b) * mul + add); x [..., C] bf16 or fp32 (last dim contiguous)."""
+    if not x.is_cuda:
+        raise RuntimeError("fwb200.ln_modulate: CUDA tensor required (no CPU fallback)")
+    C = x.shape[-1]
+    x2 = x.reshape(-1, C)
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    rows = x2.shape[0]
+    if out is None:
+        out = torch.empty((rows, C), device=x.device, dtype=torch.bfloat16)
+    o2 = out.view(-1, C)
+    _count()
+    check(lib.fwb_ln_modulate(x2.data_ptr(), _dt(x2.dtype), x2.stride(0), rows, C, float(eps), _vec(w, C, "w"),
+                              _vec(b, C, "b"), _vec(mul, C, "mul"), _vec(add, C, "add"), o2.data_ptr(), o2.stride(0),
+                              _stream()), "fwb_ln_modulate")
+    return out.view(*x.shape[:-1], C)
+
+
+def rmsnorm_rope_(x: torch.Tensor, *, w=None, eps: float = 1e-6, cos_sin=None, head_dim: int = 0) -> torch.Tensor:
+    """In place on bf16 x [rows, C] (row stride allowed): full-row RMSNorm(+w) then interleaved-pair RoPE."""
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.bfloat16 and x.is_cuda
+    rows, C = x.shape
+    if cos_sin is not None:
+        assert cos_sin.dtype == torch.float32 and cos_sin.is_contiguous() and cos_sin.shape == (rows, head_dim // 2, 2)
+    _count()
+    check(lib.fwb_rmsnorm_rope(x.data_ptr(), x.stride(0), rows, C, _vec(w, C, "w"), float(eps),
+                               None if cos_sin is None else cos_sin.data_ptr(), head_dim, _stream()), "fwb_rmsnorm_rope")
+    return x
+
+
+def ln64_rope2d_(qkv: torch.Tensor, H: int, *, eps: float, qw, qb, kw, kb, cosT, sinT) -> torch.Tensor:
+    """In place on packed qkv bf16 [rows, 3*H*64]: per-head LayerNorm + 2-D RoPE on the q and k thirds."""
+    assert qkv.dim() == 2 and qkv.stride(1) == 1 and qkv.dtype == torch.bfloat16 and qkv.is_cuda
+    rows = qkv.shape[0]
+    assert cosT.shape == (rows, 64) and sinT.shape == (rows, 64) and cosT.is_contiguous() and sinT.is_contiguous()
+    _count()
+    check(lib.fwb_ln64_rope2d(qkv.data_ptr(), qkv.stride(0), rows, H, float(eps), _vec(qw, 64, "qw"), _vec(qb, 64, "qb"),
+                              _vec(kw, 64, "kw"), _vec(kb, 64, "kb"), cosT.data_ptr(), sinT.data_ptr(), _stream()),
+          "fwb_ln64_rope2d")
+    return qkv
+
+
+def cfg_euler_step_(latents: torch.Tensor, pred_pos: torch.Tensor, pred_neg: torch.Tensor, cfg_scale: float,
+                    dsigma: float) -> torch.Tensor:
+    for t in (latents, pred_pos, pred_neg):
+        assert t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous()
+    _count()
+    check(lib.fwb_cfg_euler_step(latents.data_ptr(), pred_pos.data_ptr(), pred_neg.data_ptr(), latents.numel(),
+                                 float(cfg_scale), float(dsigma), _stream()), "fwb_cfg_euler_step")
+    return latents

@@ -73,14 +73,44 @@ int fwb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M,
  *           fusion/layer/block.py:598-605 (adapter, both directions) and vggt/layers/attention.py:61 (frame/global).
  * q,k,v,out: bf16, head_dim D in {64, 96, 128} contiguous; element strides given per tensor for batch (sb),
  * token (sl) and head (sh); all strides % 8 == 0.  scale is the softmax scale (reference: 1/sqrt(D)).
- * fp32 softmax statistics, P rounded to bf16 before PV (as flash-attn / cuDNN do), fp32 accumulation. */
+ * fp32 softmax statistics, P rounded to bf16 before PV (as flash-attn / cuDNN do), fp32 accumulation.
+ * accumulate != 0: out = bf16(out + bf16(result)) — the text + CLIP attention sum of wan_video_dit.py:197-200. */
 typedef struct {
   const void* ptr;
   int64_t sb, sl, sh;
 } fwb_tensor4_t;
 
 int fwb_attn_fwd(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v, const fwb_tensor4_t* out, int B,
-                 int H, int Lq, int Lk, int D, float scale, fwb_stream_t stream);
+                 int H, int Lq, int Lk, int D, float scale, int accumulate, fwb_stream_t stream);
+
+/* ---- K7: LayerNorm (+affine) (+modulate) -> bf16 ------------------------------------------------------------------
+ * out[r,:] = bf16( (LN(x[r,:]) * w + b) * mul + add ), any of (w,b), mul, add may be NULL.  fp32 statistics.
+ * Replaces: modulate(norm(x), shift, scale) wan_video_dit.py:69-70,301,311 (mul = 1+scale, add = shift); norm3 (:302);
+ *           Head (:353-358); vggt Block norm1/norm2 (+e-modulation) vggt/layers/block.py:73-81; adapter input norms
+ *           fusion/layer/block.py:197; img_emb LayerNorms wan_video_dit.py:324-341.
+ * x: [rows,C] bf16 or fp32 (x_dtype), C % 8 == 0, C <= 5120; vectors fp32 [C]; out bf16 [rows,C]. */
+int fwb_ln_modulate(const void* x, int x_dtype, int64_t ldx, int rows, int C, float eps, const float* w, const float* b,
+                    const float* mul, const float* add, void* out, int64_t ldo, fwb_stream_t stream);
+
+/* ---- K8+K9 (DiT / adapter): full-channel RMSNorm then interleaved-pair RoPE, in place --------------------------------
+ * x[r,:] <- rope( bf16( bf16(x * rsqrt(mean(x^2)+eps)) * w ) ), w == NULL skips the norm, cos_sin == NULL skips RoPE.
+ * cos_sin: fp32 [rows, head_dim/2, 2] = (cos, sin) of the per-token 3-D RoPE angle, shared by all heads.
+ * Replaces: RMSNorm wan_video_dit.py:135-146 (norm_q/norm_k :176-177, :192-196) and rope_apply :97-102
+ *           (DiT :178-179; adapter fusion/layer/block.py:545-550). */
+int fwb_rmsnorm_rope(void* x, int64_t ldx, int rows, int C, const float* w, float eps, const float* cos_sin, int head_dim,
+                     fwb_stream_t stream);
+
+/* ---- K8+K9 (VGGT): per-head LayerNorm(64) + 2-D rotate-half RoPE on q and k of a packed qkv buffer, in place --------
+ * qkv: bf16 [rows, 3*H*64] laid out (3, H, 64); cosT/sinT: fp32 [rows, 64] expanded tables (first 32 = y, last 32 = x).
+ * Replaces: q_norm/k_norm + rope vggt/layers/attention.py:52-58, vggt/layers/rope.py:133-188. */
+int fwb_ln64_rope2d(void* qkv, int64_t ld, int rows, int H, float eps, const float* qw, const float* qb, const float* kw,
+                    const float* kb, const float* cosT, const float* sinT, fwb_stream_t stream);
+
+/* ---- a1/a18: classifier-free guidance + flow-matching Euler update, in place on bf16 latents ------------------------
+ * latents <- latents + (neg + cfg*(pos-neg)) * dsigma with the reference's bf16 rounding after every op.
+ * Replaces: fusion/model_wan21.py:318-322, diffsynth_wan21/schedulers/flow_match.py:43-53. */
+int fwb_cfg_euler_step(void* latents, const void* pred_pos, const void* pred_neg, int64_t n, float cfg_scale, float dsigma,
+                       fwb_stream_t stream);
 
 /* ---- bring-up micro-test (tests only; pins tcgen05 descriptor encodings on hardware) ------------------------------ */
 int fwb_bringup_mma(const void* A, const void* B, float* D, int N, int K, int a_in_tmem, int b_mn_major,
