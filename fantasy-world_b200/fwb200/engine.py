@@ -42,11 +42,41 @@ def w16(owner, name, t):
     return derived(owner, "w16:" + name, lambda s: s.detach().to(BF16).reshape(s.shape[0], -1).contiguous(), t)
 
 
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
 def lin(x, layer, *, tag="", **kw):
-    """fwb200.linear on an nn.Linear's parameters (bias as cached fp32)."""
-    w = w16(layer, tag + "w", layer.weight)
-    b = f32(layer, tag + "b", layer.bias) if layer.bias is not None else None
-    return ops.linear(x, w, bias=b, **kw)
+    """fwb200.linear on an nn.Linear / 1x1 conv's parameters (bias as cached fp32).  Shapes whose N or K is not a
+    multiple of 8 (TMA needs 16-byte rows) are zero-padded — exact — and the result is sliced back."""
+    wt = layer.weight
+    N, K = wt.shape[0], wt[0].numel()
+    if N % 8 == 0 and K % 8 == 0:
+        w = w16(layer, tag + "w", wt)
+        b = f32(layer, tag + "b", layer.bias) if layer.bias is not None else None
+        return ops.linear(x, w, bias=b, **kw)
+    Np, Kp = _pad8(N), _pad8(K)
+
+    def padw(s):
+        o = torch.zeros(Np, Kp, device=s.device, dtype=BF16)
+        o[:N, :K] = s.detach().to(BF16).reshape(N, K)
+        return o
+
+    def padb(s):
+        o = torch.zeros(Np, device=s.device, dtype=torch.float32)
+        o[:N] = s.detach().float()
+        return o
+
+    w = derived(layer, tag + "wpad", padw, wt)
+    b = derived(layer, tag + "bpad", padb, layer.bias) if layer.bias is not None else None
+    assert not any(kw.get(k) is not None for k in ("scale1", "shift1", "scale2", "resid", "out")), "padded path: plain epilogue only"
+    x2 = x.reshape(-1, K)
+    if Kp != K:
+        xp = torch.zeros(x2.shape[0], Kp, device=x.device, dtype=BF16)
+        xp[:, :K] = x2
+        x2 = xp
+    y = ops.linear(x2, w, bias=b, **kw)
+    return y[:, :N].contiguous().view(*x.shape[:-1], N)
 
 
 def as_bf16(x):
@@ -75,7 +105,7 @@ def complex_to_cos_sin(freqs: torch.Tensor, device) -> torch.Tensor:
 def rope2d_expanded(pos: torch.Tensor, base: float = 100.0):
     """VGGT 2-D RoPE tables expanded per token: pos int [rows, 2] -> (cos, sin) fp32 [rows, 64].
     Same arithmetic as vggt/layers/rope.py:82-110,153-167 (fp32 angles, integer gather)."""
-    key = ("r2d", pos.data_ptr(), pos._version, tuple(pos.shape), base)
+    key = ("r2d", pos.data_ptr(), pos._version, pos.numel(), base)
     hit = _table_cache.get(key)
     if hit is None:
         p = pos.reshape(-1, 2).long()
@@ -191,10 +221,11 @@ def vggt_attn_part(block, x, tables, mods, n_batch):
     h = ops.ln_modulate(x, eps=block.norm1.eps, w=f32(block.norm1, "w", block.norm1.weight),
                         b=f32(block.norm1, "b", block.norm1.bias), mul=mul, add=add)
     qkv = lin(h, at.qkv)
-    cosT, sinT = tables
-    ops.ln64_rope2d_(qkv, H, eps=at.q_norm.eps, qw=f32(at.q_norm, "w", at.q_norm.weight),
-                     qb=f32(at.q_norm, "b", at.q_norm.bias), kw=f32(at.k_norm, "w", at.k_norm.weight),
-                     kb=f32(at.k_norm, "b", at.k_norm.bias), cosT=cosT, sinT=sinT)
+    if tables is not None:  # aggregator configuration: per-head LayerNorm(64) + 2-D RoPE on q, k
+        cosT, sinT = tables
+        ops.ln64_rope2d_(qkv, H, eps=at.q_norm.eps, qw=f32(at.q_norm, "w", at.q_norm.weight),
+                         qb=f32(at.q_norm, "b", at.q_norm.bias), kw=f32(at.k_norm, "w", at.k_norm.weight),
+                         kb=f32(at.k_norm, "b", at.k_norm.bias), cosT=cosT, sinT=sinT)
     q5 = qkv.view(n_batch, rows // n_batch, 3, H, C // H)
     o = ops.attention(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2])
     gamma = f32(block.ls1, "g", block.ls1.gamma)
