@@ -47,7 +47,7 @@ def sinusoidal_embedding_1d(dim, position):
 def precompute_freqs_cis(dim: int, end: int = 1024, theta: float = 10000.0):
     """complex128 table [end, dim // 2].  ref: wan_video_dit.py:88-94."""
     idx = torch.arange(0, dim, 2)[: dim // 2].double()
-    ang = torch.outer(torch.arange(end).double(), theta ** (-idx / dim))
+    ang = torch.outer(torch.arange(end).double(), 1.0 / (theta ** (idx / dim)))
     return torch.polar(torch.ones_like(ang), ang)
 
 

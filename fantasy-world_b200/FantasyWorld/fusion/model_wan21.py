@@ -197,24 +197,39 @@ class FantasyWorldFusionModel(nn.Module):
         clip_feature = clip_feature.to(pipe.device) if clip_feature is not None else None
         y = y.to(pipe.device) if y is not None else None
         extra = pipe.prepare_extra_input(latents)
-        sched = pipe.scheduler
         final_prediction = None
         for step in range(num_inference_steps):
-            t_host = sched.timesteps[step]
-            t = t_host.unsqueeze(0).to(dtype=pipe.torch_dtype, device=pipe.device)   # bf16 timestep, as the reference (:292-293)
-            last = step == num_inference_steps - 1
-            pred_pos, pred = self.joint_forward(latents, timestep=t, context=context_pos, clip_feature=clip_feature, y=y,
-                                                use_gradient_checkpointing=use_gradient_checkpointing, camera_token=camera_token,
-                                                plucker_fea=plucker_fea, plucker_context_lens=plucker_context_lens,
-                                                return_prediction=last, **extra)
-            if last:
+            latents, pred = self.denoise_step(latents, step, context_pos, context_neg, clip_feature=clip_feature, y=y,
+                                              camera_token=camera_token, plucker_fea=plucker_fea,
+                                              plucker_context_lens=plucker_context_lens, cfg_scale=cfg_scale,
+                                              return_prediction=(step == num_inference_steps - 1), **extra)
+            if pred is not None:
                 final_prediction = pred
-            dsigma = sched.dsigma(t_host)
-            if cfg_scale != 1.0 and context_neg is not None:
-                pred_neg, _ = self.joint_forward(latents, timestep=t, context=context_neg, clip_feature=clip_feature, y=y,
-                                                 use_gradient_checkpointing=use_gradient_checkpointing, camera_token=camera_token,
-                                                 plucker_fea=plucker_fea, plucker_context_lens=plucker_context_lens, **extra)
-                ops.cfg_euler_step_(latents, pred_pos.contiguous(), pred_neg.contiguous(), cfg_scale, dsigma)
-            else:
-                ops.cfg_euler_step_(latents, pred_pos.contiguous(), pred_pos.contiguous(), 1.0, dsigma)
         return latents, final_prediction
+
+    @torch.no_grad()
+    def denoise_step(self, latents: torch.Tensor, step: int, context_pos: torch.Tensor, context_neg: Optional[torch.Tensor] = None,
+                     clip_feature: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None, camera_token=None,
+                     plucker_fea: Optional[torch.Tensor] = None, plucker_context_lens: Optional[torch.Tensor] = None,
+                     cfg_scale: float = 5.0, return_prediction: bool = False, **extra):
+        """One iteration of the sampler loop (ref: model_wan21.py:289-322): conditional + unconditional joint_forward,
+        classifier-free guidance and the flow-matching Euler update (fused in fwb_cfg_euler_step).  `latents` may live on
+        the host (pinned): it is copied to the device here; the updated latents are returned on the device.
+        Uses the schedule set by `self.pipe.scheduler.set_timesteps`."""
+        pipe, sched = self.pipe, self.pipe.scheduler
+        dev = pipe.device
+        if latents.device.type != "cuda":
+            latents = latents.to(device=dev, dtype=torch.bfloat16, non_blocking=True)
+        latents = latents.contiguous()
+        t_host = sched.timesteps[step]
+        t = t_host.unsqueeze(0).to(dtype=pipe.torch_dtype, device=dev)   # bf16 timestep, as the reference (:292-293)
+        kw = dict(clip_feature=clip_feature, y=y, use_gradient_checkpointing=False, camera_token=camera_token,
+                  plucker_fea=plucker_fea, plucker_context_lens=plucker_context_lens)
+        pred_pos, pred = self.joint_forward(latents, timestep=t, context=context_pos, return_prediction=return_prediction, **kw, **extra)
+        dsigma = sched.dsigma(t_host)
+        if cfg_scale != 1.0 and context_neg is not None:
+            pred_neg, _ = self.joint_forward(latents, timestep=t, context=context_neg, **kw, **extra)
+            ops.cfg_euler_step_(latents, pred_pos.contiguous(), pred_neg.contiguous(), cfg_scale, dsigma)
+        else:
+            ops.cfg_euler_step_(latents, pred_pos.contiguous(), pred_pos.contiguous(), 1.0, dsigma)
+        return latents, pred

@@ -31,7 +31,9 @@ def custom_interpolate(x: torch.Tensor, size: Tuple[int, int] = None, scale_fact
 
 
 class ResidualConvUnit(nn.Module):
-    """x + conv2(act(conv1(act(x)))).  ref: dpt_head.py:395-451."""
+    """relu(x) + conv2(relu(conv1(relu(x)))).  The reference's activation is nn.ReLU(inplace=True), so by the time the
+    skip connection is added its input has already been rectified in place — the skip carries relu(x), not x.
+    ref: dpt_head.py:395-451, 342-343."""
 
     def __init__(self, features, activation, bn, groups=1):
         super().__init__()
@@ -43,9 +45,9 @@ class ResidualConvUnit(nn.Module):
         self.activation = activation
 
     def forward(self, x):
-        y = self.conv1(F.relu(x))
-        y = self.conv2(F.relu(y))
-        return y + x
+        r = F.relu(x)
+        y = self.conv2(F.relu(self.conv1(r)))
+        return y + r
 
 
 class FeatureFusionBlock(nn.Module):

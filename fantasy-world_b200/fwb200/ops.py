@@ -17,6 +17,7 @@ __all__ = [
     "ROUND_AFTER_BIAS", "ROUND_AFTER_ACT", "ROUND_AFTER_AFFINE", "ROUND_AFTER_SCALE2",
     "device_ok", "require_device", "linear", "attention", "bringup_mma",
     "ln_modulate", "rmsnorm_rope_", "ln64_rope2d_", "cfg_euler_step_", "launch_count", "reset_launch_count",
+    "prof_enable", "prof_disable",
 ]
 
 _LAUNCHES = 0
@@ -35,6 +36,48 @@ def reset_launch_count():
 def _count(n=1):
     global _LAUNCHES
     _LAUNCHES += n
+
+
+# ---- optional per-launch CUDA-event timing (bench.py: roofline of the dominant kernel, step breakdown) -------------
+_PROF = None
+
+
+def prof_enable(prefixes=None):
+    """Record a CUDA-event pair around every fwb200 launch whose tag starts with one of `prefixes` (None = all)."""
+    global _PROF
+    _PROF = {"prefixes": tuple(prefixes) if prefixes else None, "rec": {}}
+
+
+def prof_disable():
+    """Stop recording; returns {tag: (launches, total_ms)} (synchronises the device)."""
+    global _PROF
+    prof, _PROF = _PROF, None
+    if prof is None:
+        return {}
+    torch.cuda.synchronize()
+    return {tag: (len(ev), sum(a.elapsed_time(b) for a, b in ev)) for tag, ev in prof["rec"].items()}
+
+
+class _Rec:
+    __slots__ = ("tag", "a")
+
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        p = _PROF
+        self.a = None
+        if p is not None and (p["prefixes"] is None or self.tag.startswith(p["prefixes"])):
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.a is not None and _PROF is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            _PROF["rec"].setdefault(self.tag, []).append((self.a, b))
+        return False
 
 
 def device_ok() -> bool:
@@ -103,8 +146,9 @@ def linear(x: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = ACT_NONE, 
     ep.out, ep.out_ld, ep.out_dtype = out2.data_ptr(), out2.stride(0), _dt(out2.dtype)
     ep.act, ep.round_flags = act, round_flags
     _count()
-    check(lib.fwb_gemm_bf16(x2.data_ptr(), x2.stride(0), w.data_ptr(), w.stride(0), M, N, K, C.byref(ep), _stream()),
-          "fwb_gemm_bf16")
+    with _Rec(f"gemm:M{M}:N{N}:K{K}"):
+        check(lib.fwb_gemm_bf16(x2.data_ptr(), x2.stride(0), w.data_ptr(), w.stride(0), M, N, K, C.byref(ep), _stream()),
+              "fwb_gemm_bf16")
     return out.view(*x.shape[:-1], N) if out.dim() == 2 and x.dim() != 2 else out
 
 
@@ -128,8 +172,9 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
         out = torch.empty((B, Lq, H, D), device=q.device, dtype=torch.bfloat16)
     tq, tk, tv, to = _t4(q), _t4(k), _t4(v), _t4(out)
     _count()
-    check(lib.fwb_attn_fwd(C.byref(tq), C.byref(tk), C.byref(tv), C.byref(to), B, H, Lq, Lk, D, float(scale), int(accumulate),
-                           _stream()), "fwb_attn_fwd")
+    with _Rec(f"attn:B{B}:H{H}:Lq{Lq}:Lk{Lk}:D{D}"):
+        check(lib.fwb_attn_fwd(C.byref(tq), C.byref(tk), C.byref(tv), C.byref(to), B, H, Lq, Lk, D, float(scale), int(accumulate),
+                               _stream()), "fwb_attn_fwd")
     return out
 
 
@@ -161,7 +206,8 @@ def ln_modulate(x: torch.Tensor, *, eps: float, w=None, b=None, mul=None, add=No
         out = torch.empty((rows, C), device=x.device, dtype=torch.bfloat16)
     o2 = out.view(-1, C)
     _count()
-    check(lib.fwb_ln_modulate(x2.data_ptr(), _dt(x2.dtype), x2.stride(0), rows, C, float(eps), _vec(w, C, "w"),
+    with _Rec(f"ln:R{rows}:C{C}:in{x2.element_size()}"):
+      check(lib.fwb_ln_modulate(x2.data_ptr(), _dt(x2.dtype), x2.stride(0), rows, C, float(eps), _vec(w, C, "w"),
                               _vec(b, C, "b"), _vec(mul, C, "mul"), _vec(add, C, "add"), o2.data_ptr(), o2.stride(0),
                               _stream()), "fwb_ln_modulate")
     return out.view(*x.shape[:-1], C)
@@ -174,7 +220,8 @@ def rmsnorm_rope_(x: torch.Tensor, *, w=None, eps: float = 1e-6, cos_sin=None, h
     if cos_sin is not None:
         assert cos_sin.dtype == torch.float32 and cos_sin.is_contiguous() and cos_sin.shape == (rows, head_dim // 2, 2)
     _count()
-    check(lib.fwb_rmsnorm_rope(x.data_ptr(), x.stride(0), rows, C, _vec(w, C, "w"), float(eps),
+    with _Rec(f"rmsrope:R{rows}:C{C}"):
+      check(lib.fwb_rmsnorm_rope(x.data_ptr(), x.stride(0), rows, C, _vec(w, C, "w"), float(eps),
                                None if cos_sin is None else cos_sin.data_ptr(), head_dim, _stream()), "fwb_rmsnorm_rope")
     return x
 
@@ -185,7 +232,8 @@ def ln64_rope2d_(qkv: torch.Tensor, H: int, *, eps: float, qw, qb, kw, kb, cosT,
     rows = qkv.shape[0]
     assert cosT.shape == (rows, 64) and sinT.shape == (rows, 64) and cosT.is_contiguous() and sinT.is_contiguous()
     _count()
-    check(lib.fwb_ln64_rope2d(qkv.data_ptr(), qkv.stride(0), rows, H, float(eps), _vec(qw, 64, "qw"), _vec(qb, 64, "qb"),
+    with _Rec(f"ln64rope:R{rows}:H{H}"):
+      check(lib.fwb_ln64_rope2d(qkv.data_ptr(), qkv.stride(0), rows, H, float(eps), _vec(qw, 64, "qw"), _vec(qb, 64, "qb"),
                               _vec(kw, 64, "kw"), _vec(kb, 64, "kb"), cosT.data_ptr(), sinT.data_ptr(), _stream()),
           "fwb_ln64_rope2d")
     return qkv

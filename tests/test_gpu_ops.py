@@ -1,0 +1,215 @@
+"""GPU parity tests of the individual C-ABI kernels (called through ctypes — fwb200.ops) against plain fp32 torch math on
+the same bf16-rounded inputs.  Tolerances are written per test; bf16 outputs carry one rounding (2^-9 relative)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fwb():
+    import fwb200
+    fwb200.require_device()
+    return fwb200
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GEMM + epilogues
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(1, 5120, 256), (128, 256, 64), (1000, 1152, 1024), (777, 13824, 5120), (1565, 1024, 4096),
+                                   (300, 64, 5120), (4095, 5120, 144), (257, 2304, 5120)])
+def test_gemm_fp32_out_matches_fp32_reference(fwb, M, N, K):
+    torch.manual_seed(M + N + K)
+    x = _bf(torch.randn(M, K, device="cuda"))
+    w = _bf(torch.randn(N, K, device="cuda") / math.sqrt(K))
+    b = torch.randn(N, device="cuda")
+    out = fwb.linear(x, w, bias=b, out_dtype=torch.float32)
+    ref = x.float() @ w.float().t() + b
+    # fp32 accumulation in a different order: rtol 1e-3 / atol 1e-4 (the north-star tolerance) holds for fp32 outputs
+    torch.testing.assert_close(out, ref, rtol=1e-3, atol=1e-4 * math.sqrt(K / 64))
+
+
+def test_gemm_epilogue_family(fwb):
+    torch.manual_seed(3)
+    M, N, K = 515, 1024, 1024
+    x = _bf(torch.randn(M, K, device="cuda"))
+    w = _bf(torch.randn(N, K, device="cuda") / math.sqrt(K))
+    b, s1, t1, s2 = (torch.randn(N, device="cuda") for _ in range(4))
+    lin = x.float() @ w.float().t() + b
+    r16 = _bf(torch.randn(M, N, device="cuda"))
+    r32 = torch.randn(M, N, device="cuda")
+
+    def rb(t):
+        return t.to(torch.bfloat16).float()
+
+    out = fwb.linear(x, w, bias=b, act=fwb.ACT_GELU_TANH, round_flags=fwb.ROUND_AFTER_BIAS | fwb.ROUND_AFTER_ACT)
+    ref = rb(torch.nn.functional.gelu(rb(lin), approximate="tanh"))
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)   # tanh.approx + 1 bf16 ulp
+    out = fwb.linear(x, w, bias=b, act=fwb.ACT_GELU_ERF, out_dtype=torch.float32)
+    torch.testing.assert_close(out, torch.nn.functional.gelu(lin), rtol=1e-3, atol=1e-4)
+    out = fwb.linear(x, w, bias=b, act=fwb.ACT_RELU, out_dtype=torch.float32)
+    torch.testing.assert_close(out, torch.relu(lin), rtol=1e-3, atol=1e-4)
+    out = fwb.linear(x, w, bias=b, act=fwb.ACT_SILU, out_dtype=torch.float32)
+    torch.testing.assert_close(out, torch.nn.functional.silu(lin), rtol=1e-3, atol=1e-4)
+    # DiT gate + residual: bf16(x + bf16(gate * bf16(lin)))
+    out = fwb.linear(x, w, bias=b, scale1=s1, resid=r16, round_flags=fwb.ROUND_AFTER_BIAS | fwb.ROUND_AFTER_AFFINE)
+    ref = rb(r16.float() + rb(s1 * rb(lin)))
+    torch.testing.assert_close(out.float(), ref, rtol=1.6e-2, atol=1e-2)
+    # VGGT fc2: x32 + s2 * (s1 * bf16(lin) + t1)
+    out = fwb.linear(x, w, bias=b, scale1=s1, shift1=t1, scale2=s2, resid=r32, out_dtype=torch.float32, round_flags=fwb.ROUND_AFTER_BIAS)
+    ref = r32 + s2 * (s1 * rb(lin) + t1)
+    torch.testing.assert_close(out, ref, rtol=1e-3, atol=2e-2)           # a bf16 tie in rb(lin) moves the result by s1*s2*ulp
+    # strided A (a column slice of a wider buffer) and in-place residual
+    big = _bf(torch.randn(M, 2 * K, device="cuda"))
+    out = fwb.linear(big[:, K:], w, out_dtype=torch.float32)
+    torch.testing.assert_close(out, big[:, K:].float() @ w.float().t(), rtol=1e-3, atol=1e-3)
+
+
+def test_gemm_argument_errors(fwb):
+    x = _bf(torch.randn(16, 20, device="cuda"))
+    w = _bf(torch.randn(8, 20, device="cuda"))
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        fwb.linear(x, w)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------------------------
+def _attn_ref(q, k, v, scale=None):
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+    s = (qf @ kf.transpose(-1, -2)) * (scale if scale is not None else 1 / math.sqrt(q.shape[-1]))
+    return (torch.softmax(s, dim=-1) @ vf).permute(0, 2, 1, 3)
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,D", [(1, 2, 256, 256, 128), (1, 3, 1000, 777, 128), (2, 4, 300, 300, 64), (1, 12, 1560, 1565, 96),
+                                         (1, 1, 16, 21, 128), (1, 2, 1, 1, 64), (1, 2, 129, 1, 128), (3, 16, 1565, 1565, 64),
+                                         (1, 40, 520, 257, 128), (1, 2, 4095, 8190, 128)])
+def test_attention_matches_fp32_softmax(fwb, B, H, Lq, Lk, D):
+    torch.manual_seed(B * 1000 + Lq + Lk + D)
+    q, k, v = (_bf(torch.randn(B, L, H, D, device="cuda")) for L in (Lq, Lk, Lk))
+    out = fwb.attention(q, k, v)
+    ref = _attn_ref(q, k, v)
+    # P is rounded to bf16 before PV (as in flash-attn / cuDNN) and the output is bf16: 2^-8 relative on O(1) values
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=6e-3)
+    assert not torch.isnan(out.float()).any()
+
+
+def test_attention_large_logits_and_lazy_rescale(fwb):
+    """Row max that keeps growing tile after tile (sorted keys) exercises the O-rescale path; large |scores| exercise exp2 range."""
+    torch.manual_seed(0)
+    B, H, L, D = 1, 2, 1024, 128
+    q = _bf(torch.randn(B, L, H, D, device="cuda") * 3)
+    k = _bf(torch.randn(B, L, H, D, device="cuda") * torch.linspace(0.1, 4, L, device="cuda").view(1, L, 1, 1))
+    v = _bf(torch.randn(B, L, H, D, device="cuda"))
+    out = fwb.attention(q, k, v)
+    torch.testing.assert_close(out.float(), _attn_ref(q, k, v), rtol=3e-2, atol=2e-2)
+
+
+def test_attention_strided_views_and_accumulate(fwb):
+    torch.manual_seed(1)
+    B, L, H, D = 2, 333, 16, 64
+    qkv = _bf(torch.randn(B, L, 3, H, D, device="cuda"))
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    out = fwb.attention(q, k, v)
+    torch.testing.assert_close(out.float(), _attn_ref(q, k, v), rtol=2e-2, atol=6e-3)
+    # accumulate: out = bf16(out + bf16(second attention)) — the text + CLIP sum of the DiT cross attention
+    k2, v2 = _bf(torch.randn(B, 257, H, D, device="cuda")), _bf(torch.randn(B, 257, H, D, device="cuda"))
+    first = out.clone()
+    fwb.attention(q, k2, v2, out=out, accumulate=True)
+    ref = (first.float() + _attn_ref(q, k2, v2).to(torch.bfloat16).float())
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=1.2e-2)
+
+
+def test_attention_softmax_rows_sum_to_one_full_size(fwb):
+    """Size-independent property at the BASELINE C2 size (L = 32760 tokens, 128-dim heads): with V = 1 the output is 1."""
+    torch.manual_seed(2)
+    B, H, L, D = 1, 2, 32760, 128
+    q, k = _bf(torch.randn(B, L, H, D, device="cuda")), _bf(torch.randn(B, L, H, D, device="cuda"))
+    v = torch.ones(B, L, H, D, device="cuda", dtype=torch.bfloat16)
+    out = fwb.attention(q, k, v)
+    assert (out.float() - 1).abs().max() < 8e-3
+    # linearity in V: attn(q,k,2v) == 2 attn(q,k,v) exactly (power-of-two scaling commutes with every rounding)
+    v = _bf(torch.randn(B, L, H, D, device="cuda"))
+    assert torch.equal(fwb.attention(q, k, (2 * v.float()).to(torch.bfloat16)).float(), 2 * fwb.attention(q, k, v).float())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# row kernels
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,C,dtype", [(37, 5120, torch.bfloat16), (50, 1024, torch.float32), (9, 1280, torch.bfloat16),
+                                          (5, 2048, torch.float32), (3, 2560, torch.bfloat16)])
+def test_ln_modulate(fwb, rows, C, dtype):
+    torch.manual_seed(rows + C)
+    x = (torch.randn(rows, C, device="cuda") * 2 + 0.3).to(dtype)
+    w, b, mul, add = (torch.randn(C, device="cuda") for _ in range(4))
+    for kw in (dict(), dict(w=w, b=b), dict(mul=mul, add=add), dict(w=w, b=b, mul=mul, add=add)):
+        out = fwb.ln_modulate(x, eps=1e-6, **kw)
+        y = torch.nn.functional.layer_norm(x.float(), (C,), kw.get("w"), kw.get("b"), 1e-6)
+        if "mul" in kw:
+            y = y * mul + add
+        torch.testing.assert_close(out.float(), y.to(torch.bfloat16).float(), rtol=8e-3, atol=1e-2)
+        assert out.dtype == torch.bfloat16
+
+
+def test_rmsnorm_rope(fwb):
+    from oracle import fw_oracle as O
+    torch.manual_seed(5)
+    f, h, w, H, D = 2, 3, 4, 40, 128
+    L, C = f * h * w, H * D
+    x = _bf(torch.randn(L, C, device="cuda"))
+    wt = torch.randn(C, device="cuda").abs() + 0.5
+    tab = O.rope_table_3d(D, f, h, w)
+    cs = torch.stack([tab.real, tab.imag], -1).float().cuda().contiguous()
+    y = x.clone()
+    fwb.rmsnorm_rope_(y, w=wt, eps=1e-6, cos_sin=cs, head_dim=D)
+    xn = O.rms_norm(x.float().cpu()[None], wt.cpu(), 1e-6, O.BF16)
+    ref = O.rope_apply(xn, tab, H, O.BF16)[0]
+    torch.testing.assert_close(y.float().cpu(), ref, rtol=1.6e-2, atol=1.6e-2)   # 1 bf16 ulp on O(1) values
+    # rope only, head_dim 96, strided rows (the adapter's [q | v] buffer)
+    buf = _bf(torch.randn(L, 2304, device="cuda"))
+    tab96 = O.rope_table_3d(96, f, h, w)
+    cs96 = torch.stack([tab96.real, tab96.imag], -1).float().cuda().contiguous()
+    orig = buf.clone()
+    fwb.rmsnorm_rope_(buf[:, :1152], cos_sin=cs96, head_dim=96)
+    ref = O.rope_apply(orig[:, :1152].float().cpu()[None], tab96, 12, O.BF16)[0]
+    torch.testing.assert_close(buf[:, :1152].float().cpu(), ref, rtol=1.6e-2, atol=1.6e-2)
+    assert torch.equal(buf[:, 1152:], orig[:, 1152:])
+
+
+def test_ln64_rope2d(fwb):
+    from fwb200.engine import rope2d_expanded
+    from oracle import fw_oracle as O
+    torch.manual_seed(6)
+    S, hh, ww, H = 2, 3, 5, 16
+    P = 5 + hh * ww
+    sd = {"a.camera_token": torch.zeros(1, 2, 1, 1024), "a.register_token": torch.zeros(1, 2, 4, 1024)}
+    _, pos = O.aggregator_input(sd, "a", torch.zeros(1, S, hh, ww, 1024))
+    qkv = _bf(torch.randn(S * P, 3 * H * 64, device="cuda"))
+    qw, qb, kw, kb = (torch.randn(64, device="cuda") for _ in range(4))
+    cosT, sinT = rope2d_expanded(pos.cuda())
+    y = qkv.clone()
+    fwb.ln64_rope2d_(y, H, eps=1e-5, qw=qw, qb=qb, kw=kw, kb=kb, cosT=cosT, sinT=sinT)
+    q5 = qkv.float().cpu().view(S, P, 3, H, 64).permute(2, 0, 3, 1, 4)
+    q = O.rope2d_apply(O.layer_norm(q5[0], 1e-5, qw.cpu(), qb.cpu()), pos)
+    k = O.rope2d_apply(O.layer_norm(q5[1], 1e-5, kw.cpu(), kb.cpu()), pos)
+    got = y.float().cpu().view(S, P, 3, H, 64).permute(2, 0, 3, 1, 4)
+    torch.testing.assert_close(got[0], q.to(torch.bfloat16).float(), rtol=1.6e-2, atol=3e-2)
+    torch.testing.assert_close(got[1], k.to(torch.bfloat16).float(), rtol=1.6e-2, atol=3e-2)
+    assert torch.equal(got[2], q5[2])  # V untouched
+
+
+def test_cfg_euler_step(fwb):
+    torch.manual_seed(7)
+    n = 16 * 21 * 60 * 104 + 3
+    lat, p, q = (_bf(torch.randn(n, device="cuda")) for _ in range(3))
+    ref = lat.clone()
+    pred = (q + (5.0 * (p - q)))  # bf16 ops round after each step, like the reference's tensor expression
+    ref = ref + pred * torch.tensor(-0.0123)
+    fwb.cfg_euler_step_(lat, p, q, 5.0, -0.0123)
+    torch.testing.assert_close(lat.float(), ref.float(), rtol=8e-3, atol=8e-3)

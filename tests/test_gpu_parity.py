@@ -1,0 +1,178 @@
+"""GPU parity of the hot path, end to end through the reference-shaped module API (FantasyWorld.*) and the C-ABI kernels:
+
+  CUDA path (bf16)   vs   golden vectors written by the UNMODIFIED reference (CPU fp32, tools/make_golden.py)
+                     vs   the oracle with bf16 rounding emulated at the reference's autocast rounding points.
+
+Protocol: the north-star tolerance rtol=1e-3/atol=1e-4 is below one bf16 ulp (2^-8), so for bf16 tensors
+we assert (i) closeness to the bf16-emulating oracle at a few bf16 ulps, and (ii) that the error against the fp32 golden
+is bf16-sized; fp32-output kernels are held to rtol=1e-3/atol=1e-4 in test_gpu_ops.py.  Index paths are bit-exact.
+"""
+import pytest
+import torch
+
+from _common import gold, max_err, rel_err, synth_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def model():
+    """Reduced-depth (1 PCB + 1 IRG, full 14B widths) fusion model on the GPU with the per-key synthetic weights."""
+    import fwb200
+    from fwb200.synth import build_fusion_model
+    fwb200.require_device()
+    m = build_fusion_model(num_dit_layers=2, start_index=1, device="cuda", seed=0, heads=True, gen_device="cpu")
+    g = gold("joint_forward.pt")
+    m.vggt.depth_head.intermediate_layer_idx = g["head_layer_idx"]
+    m.vggt.point_head.intermediate_layer_idx = g["head_layer_idx"]
+    return m
+
+
+def _inputs(g, device="cuda", dtype=torch.bfloat16):
+    from fwb200.synth import synth_inputs
+    f, h, w = g["grid"]
+    return synth_inputs(f, h, w, device=device, seed=1024, text_len=g["text_len"], dtype=dtype)
+
+
+def test_state_dict_roundtrip_with_reference_schema(model):
+    from _common import schema
+    sd = model.state_dict()
+    assert {k: list(v.shape) for k, v in sd.items()} == schema()
+    ref_sd = synth_state_dict()
+    k = "IRGBlock.0.bicross_attention.cross_attn.m1_proj.weight"
+    assert torch.equal(sd[k].float().cpu(), ref_sd[k].to(torch.bfloat16).float())
+
+
+def test_irg_block_config1_vs_golden_and_oracle(model):
+    """BASELINE config 1 on the GPU: single IRG block forward, f,h,w = 1,4,4."""
+    from oracle import fw_oracle as O
+    g = gold("irg_block_c1.pt")
+    gen = torch.Generator().manual_seed(g["seed"])
+    f, h, w = 1, 4, 4
+    L = f * h * w
+    x_dit = torch.randn(1, L, 5120, generator=gen)
+    x_agg = torch.randn(f, 5 + h * w, 1024, generator=gen)
+    context = torch.randn(1, 257 + g["text_len"], 5120, generator=gen)
+    t_mod = torch.randn(1, 6, 5120, generator=gen) * 0.1
+    e0 = torch.randn(1, 6, 1024, generator=gen) * 0.1
+    plucker = torch.randn(1, L, 2048, generator=gen)
+    dev = "cuda"
+    fr, fd, fa = model.rope_tables(f, h, w, dev)
+    pos = model.vggt.aggregator._positions(f, h, w, torch.device(dev))
+    bf = torch.bfloat16
+    with torch.no_grad():
+        xd, xa, inter = model.IRGBlock[0](x_dit=x_dit.to(dev, bf), x_agg=x_agg.to(dev, bf), context=context.to(dev, bf),
+                                          t_mod=t_mod.to(dev, bf), freqs=fr, freqs_dit=fd, freqs_agg=fa, pos=pos, e0=e0.to(dev),
+                                          uncond=False, plucker_fea=plucker.to(dev, bf), plucker_context_lens=torch.ones(1, dtype=torch.long))
+    assert xd.dtype == torch.bfloat16 and xa.dtype == torch.float32   # the geometry stream is fp32 after modulation (Appendix A.3)
+    assert inter[0].shape == (1, f, 5 + h * w, 1024)
+    # (ii) against the reference's fp32 output: bf16-sized error
+    assert rel_err(xd.cpu(), g["x_dit_out"]) < 2e-2, rel_err(xd.cpu(), g["x_dit_out"])
+    assert rel_err(xa.cpu(), g["x_agg_out"]) < 2e-2, rel_err(xa.cpu(), g["x_agg_out"])
+    # (i) against the oracle emulating the reference's bf16 rounding points
+    sd = synth_state_dict()
+    _, opos = O.aggregator_input(sd, "vggt.aggregator", torch.zeros(1, f, h, w, 1024))
+    r = O.BF16.r
+    od, oa, _ = O.irg_block(sd, "IRGBlock.0", r(x_dit), r(x_agg), r(context), r(t_mod), O.rope_table_3d(128, f, h, w),
+                            O.rope_table_3d(96, f, h, w), O.rope_table_3d_with_extra(96, f, h, w, 5), opos, e0, r(plucker), nm=O.BF16)
+    assert rel_err(xd.cpu(), od) < 1e-2, rel_err(xd.cpu(), od)
+    assert rel_err(xa.cpu(), oa) < 1e-2, rel_err(xa.cpu(), oa)
+    # never (much) less accurate than the emulated-bf16 reference itself
+    assert rel_err(xd.cpu(), g["x_dit_out"]) < 1.5 * rel_err(od, g["x_dit_out"]) + 2e-3
+
+
+def test_joint_forward_with_heads_vs_golden(model):
+    g = gold("joint_forward.pt")
+    inp = _inputs(g)
+    f, h, w = g["grid"]
+    lens = torch.ones(f, dtype=torch.long, device="cuda")
+    lens[1:] = 4
+    ts = torch.tensor([g["timestep"]], device="cuda", dtype=torch.bfloat16)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        out, pred = model.joint_forward(inp["latents"], timestep=ts, context=inp["context_pos"], clip_feature=inp["clip_feature"],
+                                        y=inp["y"], use_gradient_checkpointing=False, plucker_fea=inp["plucker_fea"],
+                                        plucker_context_lens=lens, return_prediction=True)
+    assert out.shape == g["out"].shape == (1, 16, f, 2 * h, 2 * w)
+    e = rel_err(out.cpu(), g["out"])
+    assert e < 3e-2, e
+    for k, ref in g["pred"].items():
+        assert pred[k].shape == ref.shape, k                  # 5 frames = 4*(2-1)+1, 64x64 maps: index layout identical
+        assert torch.isfinite(pred[k].float()).all(), k
+    assert rel_err(pred["depth"].cpu(), g["pred"]["depth"]) < 8e-2
+    assert rel_err(pred["depth_conf"].cpu(), g["pred"]["depth_conf"]) < 8e-2
+    assert rel_err(pred["world_points_conf"].cpu(), g["pred"]["world_points_conf"]) < 8e-2
+    assert rel_err(pred["pose_enc"].cpu(), g["pred"]["pose_enc"]) < 8e-2
+    # second call reuses every hoisted invariant (context K/V, tables): identical result
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        out2, none = model.joint_forward(inp["latents"], timestep=ts, context=inp["context_pos"], clip_feature=inp["clip_feature"],
+                                         y=inp["y"], use_gradient_checkpointing=False, plucker_fea=inp["plucker_fea"],
+                                         plucker_context_lens=lens)
+    assert none is None and torch.equal(out, out2)
+
+
+def test_joint_forward_vs_bf16_oracle(model):
+    from oracle import fw_oracle as O
+    g = gold("joint_forward.pt")
+    inp = _inputs(g)
+    cpu = {k: v.float().cpu() for k, v in inp.items()}
+    sd = synth_state_dict()
+    ref, _, _ = O.joint_forward(sd, cpu["latents"], torch.tensor([g["timestep"]]), cpu["context_pos"], cpu["clip_feature"], cpu["y"],
+                                cpu["plucker_fea"], start_index=1, n_irg=1, nm=O.BF16)
+    ts = torch.tensor([g["timestep"]], device="cuda", dtype=torch.bfloat16)
+    with torch.no_grad():
+        out, _ = model.joint_forward(inp["latents"], timestep=ts, context=inp["context_pos"], clip_feature=inp["clip_feature"],
+                                     y=inp["y"], use_gradient_checkpointing=False, plucker_fea=inp["plucker_fea"])
+    e = rel_err(out.cpu(), ref)
+    assert e < 2e-2, e
+
+
+def test_denoise_step_and_sampler_loop(model):
+    g = gold("denoise_step.pt")
+    gj = gold("joint_forward.pt")
+    inp = _inputs(gj)
+    f, h, w = gj["grid"]
+    # 50-step schedule, run steps 0..3 through generate_video's own loop body by calling it with 4 steps is not the same
+    # schedule; so drive one step exactly as generate_video does.
+    import fwb200
+    sched = model.pipe.scheduler
+    sched.set_timesteps(50)
+    step = g["step"]
+    t = sched.timesteps[step].unsqueeze(0).to(dtype=torch.bfloat16, device="cuda")
+    lat = inp["latents"].clone()
+    with torch.no_grad():
+        p, _ = model.joint_forward(lat, timestep=t, context=inp["context_pos"], clip_feature=inp["clip_feature"], y=inp["y"],
+                                   use_gradient_checkpointing=False, plucker_fea=inp["plucker_fea"])
+        n, _ = model.joint_forward(lat, timestep=t, context=inp["context_neg"], clip_feature=inp["clip_feature"], y=inp["y"],
+                                   use_gradient_checkpointing=False, plucker_fea=inp["plucker_fea"])
+        fwb200.cfg_euler_step_(lat, p.contiguous(), n.contiguous(), 5.0, sched.dsigma(sched.timesteps[step]))
+    assert rel_err(p.cpu(), g["pred_pos"]) < 3e-2 and rel_err(n.cpu(), g["pred_neg"]) < 3e-2
+    assert rel_err(lat.cpu(), g["latents_next"]) < 1e-2
+    # the public sampler API end to end (2 steps, injected latents, camera features from the pose encoder), heads last
+    fwb200.reset_launch_count()
+    plucker = torch.randn(1, 4 * (f - 1) + 1, 16 * h, 16 * w, 6, device="cuda", dtype=torch.bfloat16)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        final, pred = model.generate_video(context_pos=inp["context_pos"], context_neg=inp["context_neg"],
+                                           clip_feature=inp["clip_feature"], y=inp["y"], height=16 * h, width=16 * w,
+                                           num_frames=4 * (f - 1) + 1, num_inference_steps=2, cfg_scale=5.0, seed=None,
+                                           latents=inp["latents"], plucker_embedding=plucker)
+    assert final.shape == inp["latents"].shape and torch.isfinite(final.float()).all()
+    assert pred is not None and pred["depth"].shape == (1, 4 * (f - 1) + 1, 16 * h, 16 * w, 1)
+    assert fwb200.launch_count() > 100   # our kernels did the work
+
+
+def test_standalone_geometry_branch(model):
+    """BASELINE config 5 analogue: VGGT.forward (aggregator without the adapter + heads) runs and is finite."""
+    torch.manual_seed(0)
+    # needs global blocks; the fusion surgery moved block 0 into the IRG block, so borrow it back for this check
+    agg = model.vggt.aggregator
+    saved = agg.global_blocks[0]
+    agg.global_blocks[0] = model.IRGBlock[0].x_agg
+    try:
+        patch = torch.randn(1, 5120, 2, 4, 4, device="cuda", dtype=torch.bfloat16)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            pred = model.vggt(patch, t=torch.tensor([500.0], device="cuda"))
+        assert pred["depth"].shape == (1, 5, 64, 64, 1) and pred["world_points"].shape == (1, 5, 64, 64, 3)
+        assert pred["pose_enc"].shape == (1, 5, 9)
+        assert all(torch.isfinite(v.float()).all() for v in pred.values())
+    finally:
+        agg.global_blocks[0] = saved
