@@ -22,8 +22,7 @@ class ModelManager:
     def load_models(self, file_paths=None, torch_dtype=None, device=None):
         from .wan_video_dit import WanModel
         dtype = torch_dtype or self.torch_dtype
-        with torch.device(device or self.device):
-            dit = WanModel(**self.dit_config)
+        dit = WanModel(**self.dit_config)   # honours an enclosing torch.device(...) context (e.g. "meta")
         dit = dit.to(dtype)
         if file_paths:
             from safetensors.torch import load_file

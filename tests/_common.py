@@ -38,3 +38,14 @@ def rel_err(a, b):
 
 def max_err(a, b):
     return float((a.float() - b.float()).abs().max())
+
+
+def assert_close_frac(out, ref, rtol, atol, loose_atol, max_bad_frac=2e-4):
+    """assert_close that tolerates a tiny fraction of elements (bf16 round-to-nearest ties that fall the other way because
+    fp32 sums were accumulated in a different order) at a looser absolute bound."""
+    out, ref = out.float(), ref.float()
+    diff = (out - ref).abs()
+    bad = diff > (atol + rtol * ref.abs())
+    frac = float(bad.float().mean())
+    assert frac <= max_bad_frac, f"{frac:.2e} of elements outside rtol={rtol} atol={atol}"
+    assert float(diff.max()) <= loose_atol, f"max abs diff {float(diff.max()):.3e} > {loose_atol}"

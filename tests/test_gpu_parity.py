@@ -165,8 +165,9 @@ def test_standalone_geometry_branch(model):
     torch.manual_seed(0)
     # needs global blocks; the fusion surgery moved block 0 into the IRG block, so borrow it back for this check
     agg = model.vggt.aggregator
-    saved = agg.global_blocks[0]
+    saved, saved_n = agg.global_blocks[0], agg.aa_block_num
     agg.global_blocks[0] = model.IRGBlock[0].x_agg
+    agg.aa_block_num = 1
     try:
         patch = torch.randn(1, 5120, 2, 4, 4, device="cuda", dtype=torch.bfloat16)
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
@@ -176,3 +177,4 @@ def test_standalone_geometry_branch(model):
         assert all(torch.isfinite(v.float()).all() for v in pred.values())
     finally:
         agg.global_blocks[0] = saved
+        agg.aa_block_num = saved_n
