@@ -73,17 +73,17 @@ class CrossAttentionAdapterProcessor(nn.Module):
 
     # loop-invariant: group1(plucker_fea) and the all-zero flag, cached per plucker tensor
     def _plucker(self, plucker_fea):
-        cache = self.__dict__.setdefault("_fwb_pl", {})
-        key = (plucker_fea.data_ptr(), plucker_fea._version, tuple(plucker_fea.shape))
-        hit = cache.get(key)
-        if hit is None:
+        cache = self.__dict__.get("_fwb_pl")
+        if cache is None:
+            cache = self.__dict__["_fwb_pl"] = E.IdCache(2)
+
+        def build():
             all_zero = bool(torch.all(plucker_fea == 0).item())
             p1 = None if all_zero else E.lin(E.as_bf16(plucker_fea).reshape(-1, plucker_fea.shape[-1]), self.k_proj.group1,
                                              round_flags=ops.ROUND_AFTER_BIAS)
-            hit = (all_zero, p1)
-            cache.clear()
-            cache[key] = hit
-        return hit
+            return all_zero, p1
+
+        return cache.get((plucker_fea, self.k_proj.group1.weight), None, build)
 
     def _shift_weights(self):
         """v_proj.group2: Linear(2048->409), ReLU, Linear(409->5120).  409 is not a multiple of 8: zero-pad to 416

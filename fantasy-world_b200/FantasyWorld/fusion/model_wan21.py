@@ -75,24 +75,14 @@ class FantasyWorldFusionModel(nn.Module):
     # ------------------------------------------------------------------------------------------------------------------
     # loop-invariant inputs
     # ------------------------------------------------------------------------------------------------------------------
-    def _cached(self, name, key, fn):
-        store = self.__dict__.setdefault("_fwb_inv", {})
-        hit = store.get(name)
-        if hit is None or hit[0] != key:
-            if name.startswith("ctx") and len(store) > 16:
-                store.clear()
-            hit = (key, fn())
-            store[name] = hit
-        return hit[1]
-
-    @staticmethod
-    def _tkey(*ts):
-        return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts if t is not None)
-
     def embed_context(self, context, clip_feature):
         """text_embedding(context) and img_emb(clip) depend only on the prompt / first frame: computed once per
-        (context, clip) pair instead of once per forward.  ref: model_wan21.py:123-128."""
+        (context, clip) tensor pair instead of once per forward.  ref: model_wan21.py:123-128."""
+        from fwb200.engine import IdCache
         dit = self.pipe.dit
+        cache = self.__dict__.get("_fwb_ctx")
+        if cache is None:
+            cache = self.__dict__["_fwb_ctx"] = IdCache(4)
 
         def build():
             ctx = dit.embed_text(context)
@@ -100,7 +90,8 @@ class FantasyWorldFusionModel(nn.Module):
                 ctx = torch.cat([dit.img_emb(clip_feature).to(ctx.dtype), ctx], dim=1)
             return ctx.contiguous()
 
-        return self._cached("ctx:%x" % context.data_ptr(), self._tkey(context, clip_feature), build)
+        srcs = (context,) + ((clip_feature,) if clip_feature is not None else ()) + (dit.text_embedding[0].weight,)
+        return cache.get(srcs, None, build)
 
     def rope_tables(self, f, h, w, device):
         """freqs (D=128), freqs_bi_dit (D=96), freqs_bi_agg (D=96 with 5 identity rotations per frame).
@@ -112,7 +103,11 @@ class FantasyWorldFusionModel(nn.Module):
             bi_agg = build_freqs_3d_with_extra_cis(self.freqs_bicross, f, h, w, n_extra=5, device=device)
             return freqs, bi_dit, bi_agg
 
-        return self._cached("rope", (f, h, w, str(device)), build)
+        store = self.__dict__.setdefault("_fwb_rope", {})
+        key = (f, h, w, str(device))
+        if key not in store:
+            store[key] = build()
+        return store[key]
 
     # ------------------------------------------------------------------------------------------------------------------
     def joint_forward(self, x: torch.Tensor, timestep: torch.Tensor, context: torch.Tensor,

@@ -18,18 +18,46 @@ BF16 = torch.bfloat16
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# derived-tensor cache (fp32 copies of bias / norm vectors, padded or concatenated weights)
+# identity caches.  Entries hold STRONG references to their source tensors and hit only on object identity + version:
+# a freed tensor's address can be handed to a new tensor by the caching allocator, so (data_ptr, shape) alone is not a
+# safe key.
 # ------------------------------------------------------------------------------------------------------------------
+class IdCache:
+    def __init__(self, max_entries=8):
+        self.max_entries = max_entries
+        self.entries = {}
+
+    def lookup(self, srcs, extra=None):
+        key = (tuple(id(s) for s in srcs), extra)
+        hit = self.entries.get(key)
+        if hit is not None and all(a is b and a._version == v for a, b, v in zip(hit[0], srcs, hit[1])):
+            return hit[2]
+        return None
+
+    def store(self, srcs, extra, value):
+        if len(self.entries) >= self.max_entries:
+            self.entries.pop(next(iter(self.entries)))
+        self.entries[(tuple(id(s) for s in srcs), extra)] = (tuple(srcs), tuple(s._version for s in srcs), value)
+        return value
+
+    def get(self, srcs, extra, fn):
+        hit = self.lookup(srcs, extra)
+        if hit is None:
+            with torch.no_grad():
+                hit = self.store(srcs, extra, fn())
+        return hit
+
+
 def derived(owner, name, fn, *srcs):
-    """Cache fn(*srcs) on `owner` (an nn.Module); recomputed when a source tensor is replaced or modified."""
+    """Cache fn(*srcs) on `owner` (an nn.Module): fp32 copies of bias / norm vectors, padded or concatenated weights.
+    Recomputed when a source tensor object is replaced or modified in place."""
     cache = owner.__dict__.setdefault("_fwb_cache", {})
-    key = tuple((s.data_ptr(), s._version, s.device, s.dtype) for s in srcs)
     hit = cache.get(name)
-    if hit is not None and hit[0] == key:
-        return hit[1]
+    if hit is not None and len(hit[0]) == len(srcs) and all(a is b and a._version == v for a, b, v in zip(hit[0], srcs, hit[1])):
+        return hit[2]
     with torch.no_grad():
         val = fn(*srcs)
-    cache[name] = (key, val)
+    cache[name] = (tuple(srcs), tuple(s._version for s in srcs), val)
     return val
 
 
@@ -86,28 +114,23 @@ def as_bf16(x):
 # ------------------------------------------------------------------------------------------------------------------
 # RoPE tables
 # ------------------------------------------------------------------------------------------------------------------
-_table_cache: dict = {}
+_cs_cache = IdCache(16)
+_r2d_cache = IdCache(8)
 
 
 def complex_to_cos_sin(freqs: torch.Tensor, device) -> torch.Tensor:
-    """complex [L, 1, hd/2] (reference layout) -> fp32 [L, hd/2, 2] (cos, sin) on `device`; cached by identity."""
-    key = ("cs", freqs.data_ptr(), freqs._version, tuple(freqs.shape), str(device))
-    hit = _table_cache.get(key)
-    if hit is None:
+    """complex [L, 1, hd/2] (reference layout) -> fp32 [L, hd/2, 2] (cos, sin) on `device`; cached per tensor object."""
+    def build():
         f = freqs.reshape(freqs.shape[0], -1)
-        hit = torch.stack([f.real, f.imag], dim=-1).to(torch.float32).contiguous().to(device)
-        if len(_table_cache) > 64:
-            _table_cache.clear()
-        _table_cache[key] = hit
-    return hit
+        return torch.stack([f.real, f.imag], dim=-1).to(torch.float32).contiguous().to(device)
+
+    return _cs_cache.get((freqs,), str(device), build)
 
 
 def rope2d_expanded(pos: torch.Tensor, base: float = 100.0):
     """VGGT 2-D RoPE tables expanded per token: pos int [rows, 2] -> (cos, sin) fp32 [rows, 64].
     Same arithmetic as vggt/layers/rope.py:82-110,153-167 (fp32 angles, integer gather)."""
-    key = ("r2d", pos.data_ptr(), pos._version, pos.numel(), base)
-    hit = _table_cache.get(key)
-    if hit is None:
+    def build():
         p = pos.reshape(-1, 2).long()
         dim = 32
         exponents = torch.arange(0, dim, 2, device=p.device).float() / dim
@@ -118,11 +141,10 @@ def rope2d_expanded(pos: torch.Tensor, base: float = 100.0):
         cos_t, sin_t = ang.cos(), ang.sin()
         cosT = torch.cat([cos_t[p[:, 0]], cos_t[p[:, 1]]], dim=-1).contiguous()
         sinT = torch.cat([sin_t[p[:, 0]], sin_t[p[:, 1]]], dim=-1).contiguous()
-        hit = (cosT, sinT)
-        if len(_table_cache) > 64:
-            _table_cache.clear()
-        _table_cache[key] = hit
-    return hit
+        return cosT, sinT
+
+    base_t = pos._base if pos._base is not None else pos   # views of one position tensor share the tables
+    return _r2d_cache.get((base_t,), (pos.numel(), base), build)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -153,10 +175,11 @@ def dit_self_attn(sa, h, cos_sin, x_resid, gate):
 
 def cross_kv(ca, context):
     """Loop-invariant K/V of the text / CLIP context — cached per context tensor."""
-    cache = ca.__dict__.setdefault("_fwb_kv", {})
-    key = (context.data_ptr(), context._version, tuple(context.shape))
-    hit = cache.get(key)
-    if hit is None:
+    cache = ca.__dict__.get("_fwb_kv")
+    if cache is None:
+        cache = ca.__dict__["_fwb_kv"] = IdCache(4)
+
+    def build():
         ctx = as_bf16(context)
         assert ctx.shape[0] == 1
         H, D = ca.num_heads, ca.head_dim
@@ -167,16 +190,16 @@ def cross_kv(ca, context):
         k = lin(txt.contiguous(), ca.k)
         ops.rmsnorm_rope_(k, w=f32(ca.norm_k, "w", ca.norm_k.weight), eps=ca.norm_k.eps)
         v = lin(txt.contiguous(), ca.v)
-        hit = [k.view(1, -1, H, D), v.view(1, -1, H, D), None, None]
+        out = [k.view(1, -1, H, D), v.view(1, -1, H, D), None, None]
         if img is not None:
             ki = lin(img.contiguous(), ca.k_img)
             ops.rmsnorm_rope_(ki, w=f32(ca.norm_k_img, "w", ca.norm_k_img.weight), eps=ca.norm_k_img.eps)
             vi = lin(img.contiguous(), ca.v_img)
-            hit[2], hit[3] = ki.view(1, -1, H, D), vi.view(1, -1, H, D)
-        if len(cache) >= 4:
-            cache.clear()
-        cache[key] = hit
-    return hit
+            out[2], out[3] = ki.view(1, -1, H, D), vi.view(1, -1, H, D)
+        return out
+
+    srcs = (context, ca.k.weight, ca.v.weight)
+    return cache.get(srcs, None, build)
 
 
 def dit_cross_attn_core(ca, n3, context):

@@ -66,6 +66,9 @@ typedef struct {
 
 int fwb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, const fwb_epilogue_t* ep,
                   fwb_stream_t stream);
+/* Test / tuning hook: force the kernel variant (-1 automatic, 0 single-CTA 128x128, 1 single-CTA 128x256,
+ * 2 CTA-pair 256x256 cta_group::2).  Results are identical across variants up to fp32 summation order. */
+int fwb_gemm_set_mode(int mode);
 
 /* ---- K1..K5: non-causal softmax attention ------------------------------------------------------------------------
  * out[b,l,h,:] = softmax_j( scale * q[b,l,h,:] . k[b,j,h,:] ) v[b,j,h,:]      (no mask, no dropout)

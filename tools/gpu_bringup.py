@@ -114,9 +114,17 @@ def _time_case(kind):
             w = torch.randn(N, K, device="cuda").to(torch.bfloat16)
             bias = torch.randn(N, device="cuda")
             out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-            ms = timeit(lambda: fwb200.linear(x, w, bias=bias, out=out))
+            res = []
+            for mode in (1, 2):
+                fwb200.lib.fwb_gemm_set_mode(mode)
+                ms = timeit(lambda: fwb200.linear(x, w, bias=bias, out=out))
+                res.append(f"mode{mode} {ms:.3f} ms {2*M*N*K/ms/1e9:.0f} TF")
+            fwb200.lib.fwb_gemm_set_mode(2)
+            ms = timeit(lambda: fwb200.linear(x, w, bias=bias, out=out, act=fwb200.ACT_GELU_ERF, round_flags=3))
+            res.append(f"mode2+gelu_erf {ms:.3f} ms")
+            fwb200.lib.fwb_gemm_set_mode(-1)
             ms_ref = timeit(lambda: torch.nn.functional.linear(x, w))
-            print(f"gemm M={M} N={N} K={K}: ours {ms:.3f} ms {2*M*N*K/ms/1e9:.1f} TFLOP/s | cublas {ms_ref:.3f} ms {2*M*N*K/ms_ref/1e9:.1f} TFLOP/s")
+            print(f"gemm M={M} N={N} K={K}: " + " | ".join(res) + f" | cublas {ms_ref:.3f} ms {2*M*N*K/ms_ref/1e9:.0f} TF")
     else:
         for (B, H, L, D) in [(1, 40, 32760, 128), (1, 16, 32865, 64), (1, 12, 32760, 96), (21, 16, 1565, 64)]:
             q = torch.randn(B, L, H, D, device="cuda").to(torch.bfloat16)
