@@ -47,7 +47,22 @@ struct AttnCfg {
   static constexpr uint32_t kColO = 256;                  // O_i at columns 256 + i*D
 };
 
-template <int D>
+// 2^x for x in [-126, 128) on the FMA / ALU pipes (no MUFU): Cody-Waite split with round-toward-minus-infinity magic
+// add, degree-3 minimax polynomial for 2^frac (max rel. error 8.6e-5 — 45x below the bf16 rounding P receives next),
+// exponent re-inserted with an integer add.  Used for a fraction of the softmax elements because MUFU.EX2
+// (16/clk/SM) is as scarce as the tensor pipe at head_dim 128 and twice as scarce at head_dim 64.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  float r;
+  asm("add.rm.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(12582912.f));   // 1.5 * 2^23: mantissa low bits = floor(x)
+  const float f = x - (r - 12582912.f);                                 // frac in [0, 1)
+  float pz = fmaf(f, 0.07706704f, 0.22764499f);
+  pz = fmaf(pz, f, 0.69511679f);
+  pz = fmaf(pz, f, 1.0f);
+  return __int_as_float(__float_as_int(pz) + (__float_as_int(r) << 23));
+}
+
+template <int D, int EMU>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -238,10 +253,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t pk[64];
 #pragma unroll
       for (int c = 0; c < 128; c += 4) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(v[c]), sl2, -m_used));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), sl2, -m_used));
-        const float p2 = fast_exp2(fmaf(__uint_as_float(v[c + 2]), sl2, -m_used));
-        const float p3 = fast_exp2(fmaf(__uint_as_float(v[c + 3]), sl2, -m_used));
+        const float x0 = fmaf(__uint_as_float(v[c]), sl2, -m_used);
+        const float x1 = fmaf(__uint_as_float(v[c + 1]), sl2, -m_used);
+        const float x2 = fmaf(__uint_as_float(v[c + 2]), sl2, -m_used);
+        const float x3 = fmaf(__uint_as_float(v[c + 3]), sl2, -m_used);
+        const float p0 = fast_exp2(x0);
+        const float p1 = (EMU >= 3) ? exp2_poly(x1) : fast_exp2(x1);
+        const float p2 = (EMU >= 2) ? exp2_poly(x2) : fast_exp2(x2);
+        const float p3 = (EMU >= 1) ? exp2_poly(x3) : fast_exp2(x3);
         a0 += p0; a1 += p1; a2 += p2; a3 += p3;
         pk[c / 2] = pack_bf16x2(p0, p1);
         pk[c / 2 + 1] = pack_bf16x2(p2, p3);
@@ -304,22 +323,40 @@ int make_qkv_map(CUtensorMap* m, const fwb_tensor4_t* t, int B, int H, int L, in
   return make_tmap_bf16(m, t->ptr, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int D>
+template <int D, int EMU>
 int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B, int H,
                 cudaStream_t stream) {
   using Cfg = AttnCfg<D>;
   static bool attr_set = false;
   if (!attr_set) {
-    FWB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    FWB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   dim3 grid((p.Lq + 2 * BQ - 1) / (2 * BQ), H, B);
-  attn_fwd_kernel<D><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  attn_fwd_kernel<D, EMU><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
   FWB_CUDA(cudaGetLastError());
   return FWB_OK;
 }
 
+template <int D>
+int launch_attn_emu(int emu, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
+                    int H, cudaStream_t stream) {
+  switch (emu) {
+    case 0: return launch_attn<D, 0>(tq, tk, tv, p, B, H, stream);
+    case 1: return launch_attn<D, 1>(tq, tk, tv, p, B, H, stream);
+    case 2: return launch_attn<D, 2>(tq, tk, tv, p, B, H, stream);
+    default: return launch_attn<D, 3>(tq, tk, tv, p, B, H, stream);
+  }
+}
+
+int g_attn_emu = -1;  // -1: per-head-dim default; 0..3: number of softmax elements out of every 4 that use exp2_poly
+
 }  // namespace
+
+extern "C" int fwb_attn_set_tuning(int exp2_poly_quarters) {
+  g_attn_emu = exp2_poly_quarters;
+  return FWB_OK;
+}
 
 extern "C" int fwb_attn_fwd(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v,
                             const fwb_tensor4_t* out, int B, int H, int Lq, int Lk, int D, float scale,
@@ -344,6 +381,6 @@ extern "C" int fwb_attn_fwd(const fwb_tensor4_t* q, const fwb_tensor4_t* k, cons
   p.Lq = Lq; p.Lk = Lk; p.d_real = D;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.accumulate = accumulate;
-  if (D == 64) return launch_attn<64>(tq, tk, tv, p, B, H, stream);
-  return launch_attn<128>(tq, tk, tv, p, B, H, stream);
+  if (D == 64) return launch_attn_emu<64>(g_attn_emu >= 0 ? g_attn_emu : 2, tq, tk, tv, p, B, H, stream);
+  return launch_attn_emu<128>(g_attn_emu >= 0 ? g_attn_emu : 1, tq, tk, tv, p, B, H, stream);
 }

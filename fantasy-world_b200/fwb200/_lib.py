@@ -50,6 +50,7 @@ def _load():
     vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
     lib.fwb_gemm_bf16.argtypes = [vp, i64, vp, i64, i32, i32, i32, C.POINTER(Epilogue), vp]
     lib.fwb_gemm_set_mode.argtypes = [i32]
+    lib.fwb_attn_set_tuning.argtypes = [i32]
     lib.fwb_attn_fwd.argtypes = [C.POINTER(Tensor4)] * 4 + [i32, i32, i32, i32, i32, f32, i32, vp]
     lib.fwb_bringup_mma.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
     lib.fwb_ln_modulate.argtypes = [vp, i32, i64, i32, i32, f32, vp, vp, vp, vp, vp, i64, vp]

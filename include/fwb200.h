@@ -86,6 +86,10 @@ typedef struct {
 int fwb_attn_fwd(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v, const fwb_tensor4_t* out, int B,
                  int H, int Lq, int Lk, int D, float scale, int accumulate, fwb_stream_t stream);
 
+/* Tuning hook: how many of every 4 softmax elements use the FMA-pipe exp2 polynomial instead of MUFU.EX2
+ * (-1 = built-in default per head_dim, 0 = MUFU only ... 3).  Changes results only below bf16 resolution of P. */
+int fwb_attn_set_tuning(int exp2_poly_quarters);
+
 /* ---- K7: LayerNorm (+affine) (+modulate) -> bf16 ------------------------------------------------------------------
  * out[r,:] = bf16( (LN(x[r,:]) * w + b) * mul + add ), any of (w,b), mul, add may be NULL.  fp32 statistics.
  * Replaces: modulate(norm(x), shift, scale) wan_video_dit.py:69-70,301,311 (mul = 1+scale, add = shift); norm3 (:302);

@@ -131,8 +131,15 @@ def _time_case(kind):
             k = torch.randn(B, L, H, D, device="cuda").to(torch.bfloat16)
             v = torch.randn(B, L, H, D, device="cuda").to(torch.bfloat16)
             out = torch.empty_like(q)
-            ms = timeit(lambda: fwb200.attention(q, k, v, out=out), iters=3, warm=1)
             fl = 4 * B * H * L * L * D
+            res = []
+            for emu in (0, 1, 2, 3):
+                fwb200.lib.fwb_attn_set_tuning(emu)
+                ms = timeit(lambda: fwb200.attention(q, k, v, out=out), iters=3, warm=1)
+                res.append(f"emu{emu} {ms:.3f} ms {fl/ms/1e9:.0f} TF")
+            fwb200.lib.fwb_attn_set_tuning(-1)
+            print("   variants: " + " | ".join(res))
+            ms = timeit(lambda: fwb200.attention(q, k, v, out=out), iters=3, warm=1)
             qt, kt, vt = (t.transpose(1, 2) for t in (q, k, v))
             ms_ref = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt), iters=3, warm=1)
             print(f"attn B={B} H={H} L={L} D={D}: ours {ms:.3f} ms {fl/ms/1e9:.1f} TFLOP/s | sdpa {ms_ref:.3f} ms {fl/ms_ref/1e9:.1f} TFLOP/s")
