@@ -58,6 +58,20 @@ def prof_disable():
     return {tag: (len(ev), sum(a.elapsed_time(b) for a, b in ev)) for tag, ev in prof["rec"].items()}
 
 
+import os as _os
+
+_DEBUG_NAN = bool(int(_os.environ.get("FWB_DEBUG_NAN", "0")))
+
+
+def _nan_check(tag, *tensors):
+    """FWB_DEBUG_NAN=1: synchronise after every launch and report the first op that produces a non-finite value."""
+    if _DEBUG_NAN:
+        torch.cuda.synchronize()
+        for i, t in enumerate(tensors):
+            if t is not None and not torch.isfinite(t.float()).all():
+                raise FloatingPointError(f"non-finite values in output {i} of {tag}")
+
+
 class _Rec:
     __slots__ = ("tag", "a")
 
@@ -149,6 +163,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, *, bias=None, act: int = ACT_NONE, 
     with _Rec(f"gemm:M{M}:N{N}:K{K}"):
         check(lib.fwb_gemm_bf16(x2.data_ptr(), x2.stride(0), w.data_ptr(), w.stride(0), M, N, K, C.byref(ep), _stream()),
               "fwb_gemm_bf16")
+    _nan_check(f"gemm:M{M}:N{N}:K{K}:act{act}", out)
     return out.view(*x.shape[:-1], N) if out.dim() == 2 and x.dim() != 2 else out
 
 
@@ -175,6 +190,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
     with _Rec(f"attn:B{B}:H{H}:Lq{Lq}:Lk{Lk}:D{D}"):
         check(lib.fwb_attn_fwd(C.byref(tq), C.byref(tk), C.byref(tv), C.byref(to), B, H, Lq, Lk, D, float(scale), int(accumulate),
                                _stream()), "fwb_attn_fwd")
+    _nan_check(f"attn:B{B}:H{H}:Lq{Lq}:Lk{Lk}:D{D}:acc{int(accumulate)}", out)
     return out
 
 
@@ -210,6 +226,7 @@ def ln_modulate(x: torch.Tensor, *, eps: float, w=None, b=None, mul=None, add=No
       check(lib.fwb_ln_modulate(x2.data_ptr(), _dt(x2.dtype), x2.stride(0), rows, C, float(eps), _vec(w, C, "w"),
                               _vec(b, C, "b"), _vec(mul, C, "mul"), _vec(add, C, "add"), o2.data_ptr(), o2.stride(0),
                               _stream()), "fwb_ln_modulate")
+    _nan_check(f"ln:R{rows}:C{C}", out)
     return out.view(*x.shape[:-1], C)
 
 
@@ -223,6 +240,7 @@ def rmsnorm_rope_(x: torch.Tensor, *, w=None, eps: float = 1e-6, cos_sin=None, h
     with _Rec(f"rmsrope:R{rows}:C{C}"):
       check(lib.fwb_rmsnorm_rope(x.data_ptr(), x.stride(0), rows, C, _vec(w, C, "w"), float(eps),
                                None if cos_sin is None else cos_sin.data_ptr(), head_dim, _stream()), "fwb_rmsnorm_rope")
+    _nan_check(f"rmsrope:R{rows}:C{C}", x)
     return x
 
 
@@ -236,6 +254,7 @@ def ln64_rope2d_(qkv: torch.Tensor, H: int, *, eps: float, qw, qb, kw, kb, cosT,
       check(lib.fwb_ln64_rope2d(qkv.data_ptr(), qkv.stride(0), rows, H, float(eps), _vec(qw, 64, "qw"), _vec(qb, 64, "qb"),
                               _vec(kw, 64, "kw"), _vec(kb, 64, "kb"), cosT.data_ptr(), sinT.data_ptr(), _stream()),
           "fwb_ln64_rope2d")
+    _nan_check(f"ln64rope:R{rows}", qkv)
     return qkv
 
 
