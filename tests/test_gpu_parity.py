@@ -88,12 +88,21 @@ def test_joint_forward_with_heads_vs_golden(model):
     lens = torch.ones(f, dtype=torch.long, device="cuda")
     lens[1:] = 4
     ts = torch.tensor([g["timestep"]], device="cuda", dtype=torch.bfloat16)
+    taps = {}
+    hooks = [model.pipe.dit.blocks[0].register_forward_hook(lambda m, i, o: taps.__setitem__("after_pcb", o.clone())),
+             model.vggt.aggregator.frame_blocks[0].register_forward_hook(lambda m, i, o: taps.__setitem__("after_frame", o.clone())),
+             model.IRGBlock[0].register_forward_hook(lambda m, i, o: taps.update(after_irg_x=o[0].clone(), after_irg_tokens=o[1].clone()))]
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         out, pred = model.joint_forward(inp["latents"], timestep=ts, context=inp["context_pos"], clip_feature=inp["clip_feature"],
                                         y=inp["y"], use_gradient_checkpointing=False, plucker_fea=inp["plucker_fea"],
                                         plucker_context_lens=lens, return_prediction=True)
+    for hk in hooks:
+        hk.remove()
     assert out.shape == g["out"].shape == (1, 16, f, 2 * h, 2 * w)
+    stage = {k: rel_err(taps[k].float().cpu().reshape(v.shape), v) for k, v in g["taps"].items()}
     e = rel_err(out.cpu(), g["out"])
+    print("stage rel errs vs reference fp32:", stage, "out", e)
+    assert all(v < 3e-2 for v in stage.values()), stage
     assert e < 3e-2, e
     for k, ref in g["pred"].items():
         assert pred[k].shape == ref.shape, k                  # 5 frames = 4*(2-1)+1, 64x64 maps: index layout identical
