@@ -127,24 +127,40 @@ def complex_to_cos_sin(freqs: torch.Tensor, device) -> torch.Tensor:
     return _cs_cache.get((freqs,), str(device), build)
 
 
+ROPE2D_FP32_ANGLES = bool(int(__import__("os").environ.get("FWB_ROPE2D_FP32_ANGLES", "0")))
+
+
 def rope2d_expanded(pos: torch.Tensor, base: float = 100.0):
     """VGGT 2-D RoPE tables expanded per token: pos int [rows, 2] -> (cos, sin) fp32 [rows, 64].
-    Same arithmetic as vggt/layers/rope.py:82-110,153-167 (fp32 angles, integer gather)."""
+    Same arithmetic as vggt/layers/rope.py:82-110,153-167 (integer gather of per-position tables).
+
+    Rounding point: the reference builds the angle table with `torch.einsum("i,j->ij", positions, inv_freq)` on first use,
+    i.e. INSIDE the sampler's `torch.cuda.amp.autocast(bf16)` region (inference_wan21.py:310), where einsum is an
+    autocast-to-bf16 op: angle = bf16(bf16(pos) * bf16(inv_freq)), then cos/sin in fp32.  That is what the released
+    weights were trained and are run with, so it is reproduced here explicitly (independent of any ambient autocast).
+    FWB_ROPE2D_FP32_ANGLES=1 (or engine.ROPE2D_FP32_ANGLES = True) selects the reference's no-autocast (fp32) arithmetic."""
+    fp32_angles = ROPE2D_FP32_ANGLES
+
     def build():
         p = pos.reshape(-1, 2).long()
         dim = 32
-        exponents = torch.arange(0, dim, 2, device=p.device).float() / dim
-        inv_freq = 1.0 / (base ** exponents)
-        max_pos = int(p.max()) + 1
-        ang = torch.einsum("i,j->ij", torch.arange(max_pos, device=p.device, dtype=inv_freq.dtype), inv_freq)
-        ang = torch.cat((ang, ang), dim=-1)
-        cos_t, sin_t = ang.cos(), ang.sin()
-        cosT = torch.cat([cos_t[p[:, 0]], cos_t[p[:, 1]]], dim=-1).contiguous()
-        sinT = torch.cat([sin_t[p[:, 0]], sin_t[p[:, 1]]], dim=-1).contiguous()
+        with torch.autocast(device_type=p.device.type, enabled=False):
+            exponents = torch.arange(0, dim, 2, device=p.device).float() / dim
+            inv_freq = 1.0 / (base ** exponents)
+            max_pos = int(p.max()) + 1
+            positions = torch.arange(max_pos, device=p.device, dtype=inv_freq.dtype)
+            if fp32_angles:
+                ang = positions[:, None] * inv_freq[None, :]
+            else:
+                ang = (positions.to(BF16)[:, None] * inv_freq.to(BF16)[None, :]).float()
+            ang = torch.cat((ang, ang), dim=-1)
+            cos_t, sin_t = ang.cos(), ang.sin()
+            cosT = torch.cat([cos_t[p[:, 0]], cos_t[p[:, 1]]], dim=-1).contiguous()
+            sinT = torch.cat([sin_t[p[:, 0]], sin_t[p[:, 1]]], dim=-1).contiguous()
         return cosT, sinT
 
     base_t = pos._base if pos._base is not None else pos   # views of one position tensor share the tables
-    return _r2d_cache.get((base_t,), (pos.numel(), base), build)
+    return _r2d_cache.get((base_t,), (pos.numel(), base, fp32_angles), build)
 
 
 # ------------------------------------------------------------------------------------------------------------------

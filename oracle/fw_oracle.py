@@ -130,19 +130,25 @@ def rope_apply(x, table, n_heads, nm=FP32):
     return nm.r(out.float())
 
 
-def rope2d_tables(dim_half, max_pos, base=100.0):
-    """vggt/layers/rope.py:82-110 (fp32 tokens): cos/sin [max_pos, dim_half] with the angle vector duplicated."""
+def rope2d_tables(dim_half, max_pos, base=100.0, nm=FP32):
+    """vggt/layers/rope.py:82-110 (fp32 tokens): cos/sin [max_pos, dim_half] with the angle vector duplicated.
+    Under CUDA autocast the einsum that forms the angles runs in bf16 (einsum is an autocast-to-bf16 op and the table is
+    built on first use inside the sampler's autocast region): angle = bf16(bf16(pos) * bf16(inv_freq))."""
     exponents = torch.arange(0, dim_half, 2).float() / dim_half
     inv_freq = 1.0 / (base ** exponents)
-    ang = torch.einsum("i,j->ij", torch.arange(max_pos, dtype=inv_freq.dtype), inv_freq)
+    positions = torch.arange(max_pos, dtype=inv_freq.dtype)
+    if nm.emulate_bf16:
+        ang = (positions.to(torch.bfloat16)[:, None] * inv_freq.to(torch.bfloat16)[None, :]).float()
+    else:
+        ang = torch.einsum("i,j->ij", positions, inv_freq)
     ang = torch.cat((ang, ang), dim=-1)
     return ang.cos(), ang.sin()
 
 
-def rope2d_apply(t, pos, base=100.0):
+def rope2d_apply(t, pos, base=100.0, nm=FP32):
     """vggt/layers/rope.py:133-188: t [B,H,N,D]; first D/2 features rotate with y, last D/2 with x; rotate-half."""
     D2 = t.shape[-1] // 2
-    cos_t, sin_t = rope2d_tables(D2, int(pos.max()) + 1, base)
+    cos_t, sin_t = rope2d_tables(D2, int(pos.max()) + 1, base, nm)
 
     def one(feat, p):
         cos = F.embedding(p, cos_t)[:, None]
@@ -245,7 +251,7 @@ def vggt_attention(sd, pfx, x, pos, nm=FP32):
     q, k, v = qkv.unbind(0)
     q = layer_norm(q, 1e-5, sd[pfx + ".q_norm.weight"], sd[pfx + ".q_norm.bias"])
     k = layer_norm(k, 1e-5, sd[pfx + ".k_norm.weight"], sd[pfx + ".k_norm.bias"])
-    q, k = rope2d_apply(q, pos), rope2d_apply(k, pos)
+    q, k = rope2d_apply(q, pos, nm=nm), rope2d_apply(k, pos, nm=nm)
     o = sdpa(q, k, v, nm).transpose(1, 2).reshape(B, N, C)
     return linear(sd, pfx + ".proj", o, nm)
 

@@ -203,7 +203,7 @@ def test_rmsnorm_rope(fwb):
 
 
 def test_ln64_rope2d(fwb):
-    from fwb200.engine import rope2d_expanded
+    import fwb200.engine as E
     from oracle import fw_oracle as O
     torch.manual_seed(6)
     S, hh, ww, H = 2, 3, 5, 16
@@ -212,7 +212,11 @@ def test_ln64_rope2d(fwb):
     _, pos = O.aggregator_input(sd, "a", torch.zeros(1, S, hh, ww, 1024))
     qkv = _bf(torch.randn(S * P, 3 * H * 64, device="cuda"))
     qw, qb, kw, kb = (torch.randn(64, device="cuda") for _ in range(4))
-    cosT, sinT = rope2d_expanded(pos.cuda())
+    E.ROPE2D_FP32_ANGLES = True   # compare with the fp32-angle oracle
+    try:
+        cosT, sinT = E.rope2d_expanded(pos.cuda())
+    finally:
+        E.ROPE2D_FP32_ANGLES = False
     y = qkv.clone()
     fwb.ln64_rope2d_(y, H, eps=1e-5, qw=qw, qb=qb, kw=kw, kb=kb, cosT=cosT, sinT=sinT)
     q5 = qkv.float().cpu().view(S, P, 3, H, 64).permute(2, 0, 3, 1, 4)

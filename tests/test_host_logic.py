@@ -48,12 +48,18 @@ def test_positions_and_token_assembly_bit_exact():
 
 
 def test_rope2d_expanded_tables_follow_reference_arithmetic():
-    from fwb200.engine import rope2d_expanded
+    import fwb200.engine as E
     pos = torch.tensor([[0, 0], [1, 1], [3, 7], [30, 52]])
-    cosT, sinT = rope2d_expanded(pos)
-    ct, st = O.rope2d_tables(32, 53)
-    assert torch.equal(cosT[:, :32], ct[pos[:, 0]]) and torch.equal(cosT[:, 32:], ct[pos[:, 1]])
-    assert torch.equal(sinT[:, :32], st[pos[:, 0]]) and torch.equal(sinT[:, 32:], st[pos[:, 1]])
+    for fp32_angles, nm in ((False, O.BF16), (True, O.FP32)):   # autocast-faithful (default) and no-autocast arithmetic
+        E.ROPE2D_FP32_ANGLES = fp32_angles
+        try:
+            with torch.autocast("cpu", dtype=torch.bfloat16):   # the result must not depend on ambient autocast
+                cosT, sinT = E.rope2d_expanded(pos.clone())
+        finally:
+            E.ROPE2D_FP32_ANGLES = False
+        ct, st = O.rope2d_tables(32, 53, nm=nm)
+        assert torch.equal(cosT[:, :32], ct[pos[:, 0]]) and torch.equal(cosT[:, 32:], ct[pos[:, 1]])
+        assert torch.equal(sinT[:, :32], st[pos[:, 0]]) and torch.equal(sinT[:, 32:], st[pos[:, 1]])
 
 
 def test_unpatchify_and_patch_unfold_layout():
