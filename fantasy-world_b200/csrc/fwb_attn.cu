@@ -349,7 +349,8 @@ int launch_attn_emu(int emu, const CUtensorMap& tq, const CUtensorMap& tk, const
   }
 }
 
-int g_attn_emu = -1;  // -1: per-head-dim default; 0..3: number of softmax elements out of every 4 that use exp2_poly
+int g_attn_emu = -1;  // -1: default (0: measured fastest on B200, the softmax is issue-bound not MUFU-bound); 0..3: number of
+                      // softmax elements out of every 4 that use exp2_poly
 
 }  // namespace
 
@@ -381,6 +382,6 @@ extern "C" int fwb_attn_fwd(const fwb_tensor4_t* q, const fwb_tensor4_t* k, cons
   p.Lq = Lq; p.Lk = Lk; p.d_real = D;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.accumulate = accumulate;
-  if (D == 64) return launch_attn_emu<64>(g_attn_emu >= 0 ? g_attn_emu : 2, tq, tk, tv, p, B, H, stream);
-  return launch_attn_emu<128>(g_attn_emu >= 0 ? g_attn_emu : 1, tq, tk, tv, p, B, H, stream);
+  if (D == 64) return launch_attn_emu<64>(g_attn_emu >= 0 ? g_attn_emu : 0, tq, tk, tv, p, B, H, stream);
+  return launch_attn_emu<128>(g_attn_emu >= 0 ? g_attn_emu : 0, tq, tk, tv, p, B, H, stream);
 }
