@@ -69,21 +69,17 @@ __device__ __forceinline__ float act_fn(float y) {
   }
 }
 
-__device__ __forceinline__ float act_dyn(float y, int act) {
-  switch (act) {
-    case FWB_ACT_GELU_TANH: return act_fn<FWB_ACT_GELU_TANH>(y);
-    case FWB_ACT_GELU_ERF: return act_fn<FWB_ACT_GELU_ERF>(y);
-    case FWB_ACT_RELU: return act_fn<FWB_ACT_RELU>(y);
-    case FWB_ACT_SILU: return act_fn<FWB_ACT_SILU>(y);
-    default: return y;
-  }
-}
-
-// Epilogue of one 32-column chunk held by one thread (one output row).  v: raw fp32 accumulators.
+// Epilogue of one 32-row x 32-column chunk owned by one warp.  Thread `lane` arrives holding the fp32 accumulators of row
+// row0+lane (TMEM 32x32b layout).  Column-wise math (bias, activation, affine) is done in that layout; the result is then
+// transposed through a 4 KB per-warp shared-memory stage (16-byte chunks XOR-swizzled by row) so that the residual read
+// and the store are coalesced: 4 (bf16) or 8 (fp32) lanes cover one row's contiguous 64 / 128 bytes instead of every lane
+// touching a different row (the row-strided 16-byte stores were the bottleneck of the short-K shapes, profiles/r01_gemm2.md).
 template <int ACT>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], int row, bool row_ok,
-                                               int colbase) {
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], int row0, int lane, int colbase,
+                                               float* stage) {
   if (colbase >= p.N) return;
+  const int row = row0 + lane;
+  const bool row_ok = row < p.M;
   float y[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) y[c] = __uint_as_float(v[c]);
@@ -136,52 +132,76 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
         for (int c = 0; c < 32; ++c) y[c] = bf16_round(y[c]);
       }
     }
-    if (!row_ok) return;
-    if (p.resid) {
-      if (p.resid_f32) {
-        const float4* r = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.resid) + (size_t)row * p.resid_ld + colbase);
+    // ---- transpose through the per-warp stage: row `lane`, 16-byte chunk c lives at chunk position c ^ (lane & 7)
+    float4* srow = reinterpret_cast<float4*>(stage + lane * 32);
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          float4 b = r[c / 4];
-          y[c] += b.x; y[c + 1] += b.y; y[c + 2] += b.z; y[c + 3] += b.w;
-        }
-      } else {
-        const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + (size_t)row * p.resid_ld + colbase);
-#pragma unroll
-        for (int c = 0; c < 32; c += 8) {
-          uint4 b = r[c / 8];
-          const uint32_t w[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            y[c + 2 * j] += __uint_as_float(w[j] << 16);
-            y[c + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
-          }
-        }
-      }
-    }
+    for (int c = 0; c < 8; ++c) srow[c ^ (lane & 7)] = make_float4(y[4 * c], y[4 * c + 1], y[4 * c + 2], y[4 * c + 3]);
+    __syncwarp();
     if (p.out_f32) {
-      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)row * p.out_ld + colbase);
+      // 8 lanes per row (4 fp32 each), 4 rows per pass
+      const int piece = lane & 7;
 #pragma unroll
-      for (int c = 0; c < 32; c += 4) o[c / 4] = make_float4(y[c], y[c + 1], y[c + 2], y[c + 3]);
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3);
+        const int grow = row0 + r;
+        float4 t = reinterpret_cast<const float4*>(stage + r * 32)[piece ^ (r & 7)];
+        if (grow < p.M) {
+          const int col = colbase + piece * 4;
+          if (p.resid) {
+            if (p.resid_f32) {
+              const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.resid) + (size_t)grow * p.resid_ld + col);
+              t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+            } else {
+              const uint2 b = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + (size_t)grow * p.resid_ld + col);
+              t.x += __uint_as_float(b.x << 16); t.y += __uint_as_float(b.x & 0xFFFF0000u);
+              t.z += __uint_as_float(b.y << 16); t.w += __uint_as_float(b.y & 0xFFFF0000u);
+            }
+          }
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)grow * p.out_ld + col) = t;
+        }
+      }
     } else {
-      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.out_ld + colbase);
+      // 4 lanes per row (8 bf16 each), 8 rows per pass
+      const int piece = lane & 3;
 #pragma unroll
-      for (int c = 0; c < 32; c += 8) {
-        uint4 w;
-        w.x = pack_bf16x2(y[c], y[c + 1]);
-        w.y = pack_bf16x2(y[c + 2], y[c + 3]);
-        w.z = pack_bf16x2(y[c + 4], y[c + 5]);
-        w.w = pack_bf16x2(y[c + 6], y[c + 7]);
-        o[c / 8] = w;
+      for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2);
+        const int grow = row0 + r;
+        const float4* sr = reinterpret_cast<const float4*>(stage + r * 32);
+        float4 a = sr[(2 * piece) ^ (r & 7)], b4 = sr[(2 * piece + 1) ^ (r & 7)];
+        if (grow < p.M) {
+          const int col = colbase + piece * 8;
+          if (p.resid) {
+            if (p.resid_f32) {
+              const float* rp = reinterpret_cast<const float*>(p.resid) + (size_t)grow * p.resid_ld + col;
+              const float4 r0 = *reinterpret_cast<const float4*>(rp), r1 = *reinterpret_cast<const float4*>(rp + 4);
+              a.x += r0.x; a.y += r0.y; a.z += r0.z; a.w += r0.w;
+              b4.x += r1.x; b4.y += r1.y; b4.z += r1.z; b4.w += r1.w;
+            } else {
+              const uint4 rb = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + (size_t)grow * p.resid_ld + col);
+              a.x += __uint_as_float(rb.x << 16); a.y += __uint_as_float(rb.x & 0xFFFF0000u);
+              a.z += __uint_as_float(rb.y << 16); a.w += __uint_as_float(rb.y & 0xFFFF0000u);
+              b4.x += __uint_as_float(rb.z << 16); b4.y += __uint_as_float(rb.z & 0xFFFF0000u);
+              b4.z += __uint_as_float(rb.w << 16); b4.w += __uint_as_float(rb.w & 0xFFFF0000u);
+            }
+          }
+          uint4 w;
+          w.x = pack_bf16x2(a.x, a.y);
+          w.y = pack_bf16x2(a.z, a.w);
+          w.z = pack_bf16x2(b4.x, b4.y);
+          w.w = pack_bf16x2(b4.z, b4.w);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)grow * p.out_ld + col) = w;
+        }
       }
     }
+    __syncwarp();   // the stage is reused by the next chunk
   } else if (row_ok) {
     // ragged N tail: scalar path
 #pragma unroll 1
     for (int c = 0; c < 32; ++c) {
       const int col = colbase + c;
       if (col >= p.N) break;
-      float t = y[c];
+      float t = __uint_as_float(v[c]);
       if (p.bias) t += p.bias[col];
       if (p.round_flags & 1) t = bf16_round(t);
       if (ACT != FWB_ACT_NONE) {
@@ -207,6 +227,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   }
 }
 
+constexpr int kStageFloats = 32 * 32;           // per-warp transpose stage (4 KB)
+constexpr int kEpiStageBytes = 8 * kStageFloats * 4;
+
 // =====================================================================================================================
 // single-CTA kernel: 128 x BN tiles
 // =====================================================================================================================
@@ -214,7 +237,7 @@ template <int BN>
 struct GemmCfg {
   static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024;
 };
 
 template <int BN, int ACT>
@@ -307,14 +330,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
-      const int row = tm * BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
+      float* stage = reinterpret_cast<float*>(smem + ST * Cfg::kStageBytes) + e * kStageFloats;
 #pragma unroll 1
       for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((q * 32) << 16) + acc * BN + half * COLS_PER_WARP + c0, v);
         tmem_ld_wait();
-        epilogue_chunk<ACT>(p, v, row, row_ok, tn * BN + half * COLS_PER_WARP + c0);
+        epilogue_chunk<ACT>(p, v, tm * BM + q * 32, lane, tn * BN + half * COLS_PER_WARP + c0, stage);
       }
       tc_fence_before();
       __syncwarp();
@@ -332,7 +354,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // =====================================================================================================================
 constexpr int kStages2 = 6;
 constexpr int kStageBytes2 = BM * BK * 2 + 128 * BK * 2;  // this CTA's 128 rows of A + its 128 rows of W
-constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024;
+constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + kEpiStageBytes + 1024;
 
 template <int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
@@ -427,14 +449,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t acc = lt & 1, aph = (lt >> 1) & 1;
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
-      const int row = tm * 256 + rank * 128 + q * 32 + lane;
-      const bool row_ok = row < p.M;
+      float* stage = reinterpret_cast<float*>(smem + ST * kStageBytes2) + e * kStageFloats;
 #pragma unroll 1
       for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((q * 32) << 16) + acc * BN + half * COLS_PER_WARP + c0, v);
         tmem_ld_wait();
-        epilogue_chunk<ACT>(p, v, row, row_ok, tn * BN + half * COLS_PER_WARP + c0);
+        epilogue_chunk<ACT>(p, v, tm * 256 + rank * 128 + q * 32, lane, tn * BN + half * COLS_PER_WARP + c0, stage);
       }
       tc_fence_before();
       __syncwarp();
