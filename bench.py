@@ -175,7 +175,10 @@ def run_ours(args):
     n_pcb, n_irg = args.pcb, args.irg
     model = build_fusion_model(num_dit_layers=n_pcb + n_irg, start_index=n_pcb, device=dev, seed=0, heads=False)
     model.pipe.device = dev
-    inp = synth_inputs(f, h, w, device=dev, seed=1024 + rank, text_len=512)
+    inp = synth_inputs(f, h, w, device=dev, seed=1024, text_len=512)       # one sample, replicated inputs
+    if world > 1:
+        from fwb200.sp import SPContext
+        model.sp = SPContext()                                               # tokens sharded over the ranks
     lens = torch.ones(f, dtype=torch.long, device=dev)
     lens[1:] = 4
     sched = model.pipe.scheduler
@@ -198,7 +201,7 @@ def run_ours(args):
 
     # ---- timed region: device-resident inputs --------------------------------------------------------------------------
     L = f * h * w
-    dom_tag = f"attn:B1:H40:Lq{L}:Lk{L}:D128"
+    dom_tag = f"attn:B1:H40:Lq{L // world}:Lk{L}:D128"
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -250,14 +253,14 @@ def run_ours(args):
 
     if rank != 0:
         return
-    steps_per_s = world * args.steps / (ms / 1e3)       # weak scaling: every rank denoises its own sample
-    e2e_sps = world * args.steps / (ms_e2e / 1e3)
+    steps_per_s = args.steps / (ms / 1e3)               # strong scaling: all ranks denoise ONE sample (sequence parallel)
+    e2e_sps = args.steps / (ms_e2e / 1e3)
     burst, sustained, peak_src = peaks()
     roof = None
     if dom_tag in prof:
         cnt, tot = prof[dom_tag]
         per = tot / cnt
-        fl = 4.0 * 40 * L * L * 128
+        fl = 4.0 * 40 * (L // world) * L * 128
         ach = fl / (per * 1e-3) / 1e12
         traffic = None
         tp = ROOT / "profiles" / "attn_d128_dram_bytes.json"
@@ -280,13 +283,15 @@ def run_ours(args):
                "sample_seconds": dt, "achieved_tflops": rate / 1e12}
     full = (f, h, w, n_pcb, n_irg) == (21, 30, 52, 16, 24)
     line = {"metric": "denoise_steps_per_sec", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": ("Wan2.1-I2V-14B-480P shape (BASELINE configs[1]): " if full else "REDUCED (not the headline config): ") +
                        f"latents 1x16x{f}x{2 * h}x{2 * w}, {n_pcb} PCB + {n_irg} IRG blocks, 2 forwards/step (CFG 5.0), random-init",
                        "tokens_video": L, "tokens_geometry": f * (5 + h * w), "flop_per_step": 2 * fwd_fl,
-                       "achieved_tflops_per_gpu": 2 * fwd_fl * args.steps / (ms / 1e3) / 1e12,
-                       "parallelism": "replicas" if world > 1 else "single",
+                       "achieved_tflops_per_gpu": 2 * fwd_fl * args.steps / (ms / 1e3) / 1e12 / world,
+                       "parallelism": f"sp{world} (token-sharded sequence parallel, 1 all-gather of packed K|V per attention)" if world > 1 else "single",
+                       "sp_gathers_per_step": (model.sp.n_gathers / max(1, args.warmup + 2 * args.steps)) if world > 1 else 0,
+                       "sp_gather_bytes_per_step": (model.sp.gather_bytes / max(1, args.warmup + 2 * args.steps)) if world > 1 else 0,
                        "l2": "per-step working set (37 GB weights + >1 GB activations) exceeds the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_sps, "unit": "steps/s", "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                     "api": "FantasyWorldFusionModel.denoise_step from pinned host latents; conditioning uploaded once per run inside the timed region"},

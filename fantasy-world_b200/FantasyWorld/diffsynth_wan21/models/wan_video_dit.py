@@ -225,6 +225,9 @@ class DiTBlock(nn.Module):
 
         mods = E.dit_mod_vectors(self, t_mod)
         cs = E.complex_to_cos_sin(freqs, x.device)
+        if E.SP is not None and cs.shape[0] != s:      # sequence parallel: x holds this rank's rows of the token grid
+            r0, r1 = E.SP.layout.video_range(E.SP.rank)
+            cs = cs[r0:r1]
         h = ops.ln_modulate(xs, eps=self.norm1.eps, mul=mods["mul_msa"], add=mods["shift_msa"])
         xs = E.dit_self_attn(self.self_attn, h, cs, xs, mods["gate_msa"])
         n3 = ops.ln_modulate(xs, eps=self.norm3.eps, w=E.f32(self.norm3, "w", self.norm3.weight),

@@ -68,7 +68,14 @@ class CrossModalityBiAttentionBlock(nn.Module):
         assert x1.shape[0] == 1 and x2.shape[0] == 1, "fused path: batch 1"
         a = E.as_bf16(x1)[0]
         g = x2[0] if x2.dtype in (torch.float32, torch.bfloat16) else x2[0].float()
-        a, g = E.bicross(self, a, g, E.complex_to_cos_sin(freqs_dit, x1.device), E.complex_to_cos_sin(freqs_agg, x1.device))
+        cs_dit, cs_agg = E.complex_to_cos_sin(freqs_dit, x1.device), E.complex_to_cos_sin(freqs_agg, x1.device)
+        if E.SP is not None:   # sequence parallel: both streams hold this rank's rows only
+            lay, rk = E.SP.layout, E.SP.rank
+            if cs_dit.shape[0] != a.shape[0]:
+                cs_dit = cs_dit[slice(*lay.video_range(rk))]
+            if cs_agg.shape[0] != g.shape[0]:
+                cs_agg = cs_agg[slice(*lay.geo_range(rk))]
+        a, g = E.bicross(self, a, g, cs_dit, cs_agg)
         return a.unsqueeze(0), g.unsqueeze(0)
 
 
@@ -93,7 +100,11 @@ class IRGBlock(nn.Module):
         B = x_dit.size(0)
         xd, mod_dit = self.x_dit(x_dit, context, t_mod, freqs, return_partial=True, **kwargs)
         pos_g = pos.reshape(B, -1, pos.shape[-1])
-        xa, mod_agg = self.x_agg(x_agg.reshape(B, -1, D), pos=pos_g, e0=e0, return_partial=True)
+        E.SP_GLOBAL_ATTN = True     # (only consulted under sequence parallelism) this VGGT block attends over ALL frames
+        try:
+            xa, mod_agg = self.x_agg(x_agg.reshape(B, -1, D), pos=pos_g, e0=e0, return_partial=True)
+        finally:
+            E.SP_GLOBAL_ATTN = False
         if uncond is not True:
             xd, xa = self.bicross_attention([xd, xa], freqs=freqs, freqs_dit=freqs_dit, freqs_agg=freqs_agg)
         xd = self.x_dit(xd, context, t_mod, freqs, run_remaining=True, modifiers=mod_dit, **kwargs)

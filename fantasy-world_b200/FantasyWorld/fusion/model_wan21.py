@@ -114,8 +114,12 @@ class FantasyWorldFusionModel(nn.Module):
                       clip_feature: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None,
                       use_gradient_checkpointing: bool = True, camera_token=None, plucker_fea: Optional[torch.Tensor] = None,
                       plucker_context_lens: Optional[torch.Tensor] = None, uncond=False, return_prediction=False, **kwargs):
-        """One denoiser evaluation.  ref: model_wan21.py:104-224."""
+        """One denoiser evaluation.  ref: model_wan21.py:104-224.  With `self.sp` set (fwb200.sp.SPContext) the tokens are
+        sharded over the ranks of that group (see _joint_forward_sp); inputs and outputs are replicated either way."""
         ops.require_device()
+        if getattr(self, "sp", None) is not None and self.sp.world > 1:
+            return self._joint_forward_sp(x, timestep, context, clip_feature, y, camera_token, plucker_fea, plucker_context_lens,
+                                          uncond, return_prediction)
         dit, vggt, agg = self.pipe.dit, self.vggt, self.vggt.aggregator
         t, t_mod = dit.embed_time(timestep)
         ctx = self.embed_context(context, clip_feature)
@@ -153,6 +157,82 @@ class FantasyWorldFusionModel(nn.Module):
         if return_prediction:
             return x, vggt._head_predction(patch_token, agg.patch_start_idx, output_list)
         return x, None
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _local_rows(self, t: torch.Tensor, r0: int, r1: int):
+        """Cached row slice t[:, r0:r1] of a loop-invariant [1, L, C] tensor (stable identity keeps downstream caches warm)."""
+        from fwb200.engine import IdCache
+        cache = self.__dict__.get("_fwb_rows")
+        if cache is None:
+            cache = self.__dict__["_fwb_rows"] = IdCache(4)
+        return cache.get((t,), (r0, r1), lambda: t[:, r0:r1].contiguous())
+
+    def _joint_forward_sp(self, x, timestep, context, clip_feature, y, camera_token, plucker_fea, plucker_context_lens, uncond,
+                          return_prediction):
+        """Sequence-parallel joint_forward.  Video tokens: contiguous L/P rows per rank.  Geometry tokens:
+        frame-aligned shards.  Collectives per forward: one all-gather of packed K|V per attention (40 DiT self-attentions,
+        24 VGGT global attentions, 2 x 24 adapter directions), one gather of the 1024-wide projected tokens, one gather of the
+        64-wide head output.  Weights are replicated."""
+        import fwb200.engine as E
+        sp = self.sp
+        dit, vggt, agg = self.pipe.dit, self.vggt, self.vggt.aggregator
+        assert camera_token is None, "camera_token conditioning is not sharded (not used by the sampler)"
+        t, t_mod = dit.embed_time(timestep)
+        ctx = self.embed_context(context, clip_feature)
+        if dit.has_image_input:
+            x = torch.cat([x, y], dim=1)
+        b, cin, F_, H_, W_ = x.shape
+        pf, ph, pw = dit.patch_size
+        f, h, w = F_ // pf, H_ // ph, W_ // pw
+        lay = sp.set_grid(f, h, w)
+        r0, r1 = lay.video_range(sp.rank)
+        f0, f1 = lay.frame_range(sp.rank)
+        # patchify only this rank's rows of the (f h w) token grid
+        cols = E.as_bf16(x).view(b, cin, f, pf, h, ph, w, pw).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(f * h * w, cin * pf * ph * pw)
+        xl = E.lin(cols[r0:r1].contiguous(), dit.patch_embedding, round_flags=ops.ROUND_AFTER_BIAS).unsqueeze(0)
+        freqs, freqs_bi_dit, freqs_bi_agg = self.rope_tables(f, h, w, xl.device)
+        kw = dict(plucker_fea=self._local_rows(plucker_fea, r0, r1) if plucker_fea is not None else None,
+                  plucker_context_lens=plucker_context_lens)
+        E.SP = sp
+        try:
+            for i in range(self.start_index):
+                xl = dit.blocks[i](xl, ctx, t_mod, freqs, **kw)
+            # 5120 -> 1024 projection on local rows, then one gather so that every rank can pick its frames
+            proj = sp.all_gather_rows(vggt.project_tokens(xl)[0], lay.video_rows)              # [L, 1024]
+            patch_local = proj.view(f, h, w, -1)[f0:f1].unsqueeze(0)                            # [1, f_loc, h, w, 1024]
+            e0 = vggt.time_modulation(timestep)
+            tokens, pos = agg._process_aggregator_input(patch_local, None, frame_range=(f0, f1))
+            S, (_, P, C) = f1 - f0, tokens.shape
+            frame_idx = global_idx = 0
+            keep = None
+            if return_prediction:
+                n_layers = len(dit.blocks) - self.start_index
+                keep = {n_layers - 1}
+                for head in (vggt.depth_head, vggt.point_head):
+                    if head is not None:
+                        keep |= {li % n_layers for li in head.intermediate_layer_idx}
+            output_list = []
+            for i in range(len(dit.blocks) - self.start_index):
+                tokens, frame_idx, frame_inter = agg._process_frame_attention(tokens, 1, S, P, C, frame_idx, pos=pos, e0=e0)
+                assert i in self.cross_attention_list, "sequence parallel path expects every post-PCB block to be an IRG block"
+                xl, tokens, global_inter = self.IRGBlock[i](x_dit=xl, x_agg=tokens, context=ctx, t_mod=t_mod, freqs=freqs,
+                                                            freqs_dit=freqs_bi_dit, freqs_agg=freqs_bi_agg, pos=pos, e0=e0,
+                                                            uncond=uncond, **kw)
+                global_idx += 1
+                if return_prediction:
+                    if i in keep:   # gather the [rows, 2C] intermediates the heads read; the others are never touched
+                        loc = torch.cat([frame_inter[0].reshape(S * P, C), global_inter[0].reshape(S * P, C)], dim=-1).contiguous()
+                        output_list.append(sp.all_gather_rows(loc, lay.geo_rows()).view(1, f, P, 2 * C))
+                    else:
+                        output_list.append(None)
+            out_local = dit.head(xl, t)[0]                                                       # [L/P, 64]
+        finally:
+            E.SP = None
+        out = dit.unpatchify(sp.all_gather_rows(out_local.contiguous(), lay.video_rows).unsqueeze(0), (f, h, w))
+        if return_prediction:
+            patch_token = proj.view(1, f, h, w, -1)
+            return out, vggt._head_predction(patch_token, agg.patch_start_idx, output_list)
+        return out, None
 
     # ------------------------------------------------------------------------------------------------------------------
     @torch.no_grad()

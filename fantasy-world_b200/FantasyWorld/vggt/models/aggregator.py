@@ -56,16 +56,25 @@ class Aggregator(nn.Module):
         self.use_reentrant = False
 
     # -- token assembly ------------------------------------------------------------------------------------------------
-    def _process_aggregator_input(self, patch_tokens: torch.Tensor, camera_token: torch.Tensor = None):
+    def _process_aggregator_input(self, patch_tokens: torch.Tensor, camera_token: torch.Tensor = None, frame_range=None):
         """patch_tokens [B, T, h, w, C] -> tokens [(B T), 5 + h*w, C], pos int64 [(B T), 5 + h*w, 2]
-        (patch positions shifted by +1, specials at (0, 0)).  ref: aggregator.py:261-281."""
+        (patch positions shifted by +1, specials at (0, 0)).  ref: aggregator.py:261-281.
+        `frame_range=(f0, f1)` (sequence parallelism, B == 1): patch_tokens holds only frames f0..f1 of the clip; the
+        "first frame" variants of the camera / register tokens are used for global frame 0 only."""
         B, T, gh, gw, C = patch_tokens.shape
         flat = patch_tokens.reshape(B * T, gh * gw, C)
-        if camera_token is not None:
-            cam = self.CamTokenProjector(camera_token).to(flat.dtype)
+        if frame_range is None:
+            if camera_token is not None:
+                cam = self.CamTokenProjector(camera_token).to(flat.dtype)
+            else:
+                cam = slice_expand_and_flatten(self.camera_token, B, T).to(flat.dtype)
+            reg = slice_expand_and_flatten(self.register_token, B, T).to(flat.dtype)
         else:
-            cam = slice_expand_and_flatten(self.camera_token, B, T).to(flat.dtype)
-        reg = slice_expand_and_flatten(self.register_token, B, T).to(flat.dtype)
+            assert B == 1 and camera_token is None
+            f0, f1 = frame_range
+            slot = torch.tensor([0 if fr == 0 else 1 for fr in range(f0, f1)], device=flat.device)
+            cam = self.camera_token[0, slot].to(flat.dtype)       # [T, 1, C]
+            reg = self.register_token[0, slot].to(flat.dtype)     # [T, 4, C]
         tokens = torch.cat([cam, reg, flat], dim=1)
         return tokens, self._positions(B * T, gh, gw, flat.device)
 

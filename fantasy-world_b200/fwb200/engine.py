@@ -16,6 +16,10 @@ from .ops import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_RELU, ACT_SILU, ROUND_AFTER_A
 
 BF16 = torch.bfloat16
 
+# Sequence-parallel context (fwb200.sp.SPContext) for the duration of a joint_forward, or None on a single GPU.
+SP = None
+SP_GLOBAL_ATTN = False   # set by IRGBlock around the VGGT *global* block so that it gathers K|V across ranks
+
 
 # ------------------------------------------------------------------------------------------------------------------
 # identity caches.  Entries hold STRONG references to their source tensors and hit only on object identity + version:
@@ -180,13 +184,27 @@ def dit_self_attn(sa, h, cos_sin, x_resid, gate):
     """x_resid + gate * o(attn(rope(norm_q(q(h))), rope(norm_k(k(h))), v(h)))  — wan_video_dit.py:175-182, 301."""
     L = h.shape[0]
     H, D = sa.num_heads, sa.head_dim
+    C = H * D
     q = lin(h, sa.q)
-    k = lin(h, sa.k)
-    v = lin(h, sa.v)
-    ops.rmsnorm_rope_(q, w=f32(sa.norm_q, "w", sa.norm_q.weight), eps=sa.norm_q.eps, cos_sin=cos_sin, head_dim=D)
-    ops.rmsnorm_rope_(k, w=f32(sa.norm_k, "w", sa.norm_k.weight), eps=sa.norm_k.eps, cos_sin=cos_sin, head_dim=D)
-    o = ops.attention(q.view(1, L, H, D), k.view(1, L, H, D), v.view(1, L, H, D))
-    return lin(o.view(L, H * D), sa.o, scale1=gate, resid=x_resid, round_flags=ROUND_AFTER_BIAS | ROUND_AFTER_AFFINE)
+    if SP is None:
+        k = lin(h, sa.k)
+        v = lin(h, sa.v)
+        ops.rmsnorm_rope_(q, w=f32(sa.norm_q, "w", sa.norm_q.weight), eps=sa.norm_q.eps, cos_sin=cos_sin, head_dim=D)
+        ops.rmsnorm_rope_(k, w=f32(sa.norm_k, "w", sa.norm_k.weight), eps=sa.norm_k.eps, cos_sin=cos_sin, head_dim=D)
+        o = ops.attention(q.view(1, L, H, D), k.view(1, L, H, D), v.view(1, L, H, D))
+    else:
+        # sequence parallel: h holds this rank's L/P tokens.  K and V are written side by side into one packed buffer so
+        # that a single all-gather moves both; queries stay local.
+        kv = torch.empty((L, 2 * C), device=h.device, dtype=BF16)
+        lin(h, sa.k, out=kv[:, :C])
+        lin(h, sa.v, out=kv[:, C:])
+        ops.rmsnorm_rope_(q, w=f32(sa.norm_q, "w", sa.norm_q.weight), eps=sa.norm_q.eps, cos_sin=cos_sin, head_dim=D)
+        ops.rmsnorm_rope_(kv[:, :C], w=f32(sa.norm_k, "w", sa.norm_k.weight), eps=sa.norm_k.eps, cos_sin=cos_sin, head_dim=D)
+        kv_all = SP.all_gather_rows(kv, SP.layout.video_rows)
+        Lk = kv_all.shape[0]
+        o = ops.attention(q.view(1, L, H, D), kv_all[:, :C].unflatten(1, (H, D)).unsqueeze(0),
+                          kv_all[:, C:].unflatten(1, (H, D)).unsqueeze(0))
+    return lin(o.view(L, C), sa.o, scale1=gate, resid=x_resid, round_flags=ROUND_AFTER_BIAS | ROUND_AFTER_AFFINE)
 
 
 def cross_kv(ca, context):
@@ -266,7 +284,13 @@ def vggt_attn_part(block, x, tables, mods, n_batch):
                          qb=f32(at.q_norm, "b", at.q_norm.bias), kw=f32(at.k_norm, "w", at.k_norm.weight),
                          kb=f32(at.k_norm, "b", at.k_norm.bias), cosT=cosT, sinT=sinT)
     q5 = qkv.view(n_batch, rows // n_batch, 3, H, C // H)
-    o = ops.attention(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2])
+    if SP is not None and SP_GLOBAL_ATTN:
+        # global attention under sequence parallelism: local queries, K|V gathered from the frame-aligned shards
+        kv_all = SP.all_gather_rows(qkv[:, C:].contiguous(), SP.layout.geo_rows())
+        o = ops.attention(q5[:, :, 0], kv_all[:, :C].unflatten(1, (H, C // H)).unsqueeze(0),
+                          kv_all[:, C:].unflatten(1, (H, C // H)).unsqueeze(0))
+    else:
+        o = ops.attention(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2])
     gamma = f32(block.ls1, "g", block.ls1.gamma)
     return lin(o.view(rows, C), at.proj, scale1=gamma, resid=x, out_dtype=x.dtype,
                round_flags=ROUND_AFTER_BIAS | ROUND_AFTER_AFFINE)
@@ -308,8 +332,18 @@ def bicross(blk, x1, x2, cs_dit, cs_agg):
     v1 = qv1[:, E:].unflatten(1, (H, D)).unsqueeze(0)
     k = kv2[:, :E].unflatten(1, (H, D)).unsqueeze(0)
     v2 = kv2[:, E:].unflatten(1, (H, D)).unsqueeze(0)
-    o1 = ops.attention(q, k, v2)   # video <- geometry
-    o2 = ops.attention(k, q, v1)   # geometry <- video
+    if SP is None:
+        o1 = ops.attention(q, k, v2)   # video <- geometry
+        o2 = ops.attention(k, q, v1)   # geometry <- video
+    else:
+        qv1_all = SP.all_gather_rows(qv1, SP.layout.video_rows)      # [L, 2E]
+        kv2_all = SP.all_gather_rows(kv2, SP.layout.geo_rows())      # [N, 2E]
+
+        def heads(t):
+            return t.unflatten(1, (H, D)).unsqueeze(0)
+
+        o1 = ops.attention(q, heads(kv2_all[:, :E]), heads(kv2_all[:, E:]))   # local video queries x all geometry keys
+        o2 = ops.attention(k, heads(qv1_all[:, :E]), heads(qv1_all[:, E:]))   # local geometry queries x all video keys
     rf = ROUND_AFTER_BIAS | ROUND_AFTER_AFFINE
     x1 = lin(o1.view(L1, E), ca.out_m1_proj, scale1=f32(blk, "g1", blk.gamma_m1), resid=x1, round_flags=rf)
     x2 = lin(o2.view(L2, E), ca.out_m2_proj, scale1=f32(blk, "g2", blk.gamma_m2), resid=x2, out_dtype=x2.dtype,

@@ -1,0 +1,118 @@
+"""Sequence parallelism for the denoising hot path: one process per GPU, tokens sharded across ranks,
+weights replicated, ONE all-gather of packed K|V per attention.
+
+  video tokens     contiguous (f h w) order, L / P rows per rank (L % P == 0 at the BASELINE sizes: 32760 = 8 * 4095)
+  geometry tokens  frame-aligned shards (21 frames over 8 ranks -> 3,3,3,3,3,2,2,2) so the per-frame attention of the
+                   VGGT frame blocks needs no communication; global attention and the adapter only need
+                   "local queries x all keys", so the two streams may be partitioned differently
+  everything else  (LayerNorm, modulation, GEMMs, RoPE, gates, text/CLIP cross-attention against the replicated context,
+                   camera AdaLN with token-aligned features) is token-local
+
+The reference has no live multi-GPU path (its Ulysses hooks import a module that is not in the tree);
+this is new functionality.  Collectives go through torch.distributed (NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def split_even(n: int, parts: int) -> List[int]:
+    """Sizes of `parts` contiguous shards of n items, the first (n % parts) shards one larger."""
+    base, rem = divmod(n, parts)
+    return [base + (1 if r < rem else 0) for r in range(parts)]
+
+
+def offsets(sizes: List[int]) -> List[int]:
+    out, acc = [], 0
+    for s in sizes:
+        out.append(acc)
+        acc += s
+    return out
+
+
+@dataclass
+class SPLayout:
+    """Static description of how one (f, h, w) token grid is sharded over `world` ranks."""
+    world: int
+    f: int
+    h: int
+    w: int
+    n_special: int = 5
+    video_rows: List[int] = field(default_factory=list)     # rows per rank (video stream)
+    frames: List[int] = field(default_factory=list)         # frames per rank (geometry stream)
+
+    def __post_init__(self):
+        L = self.f * self.h * self.w
+        self.video_rows = split_even(L, self.world)
+        self.frames = split_even(self.f, self.world)
+        self.P = self.n_special + self.h * self.w           # tokens per frame (geometry)
+
+    @property
+    def L(self):
+        return self.f * self.h * self.w
+
+    @property
+    def N(self):
+        return self.f * self.P
+
+    def video_range(self, rank) -> Tuple[int, int]:
+        o = offsets(self.video_rows)[rank]
+        return o, o + self.video_rows[rank]
+
+    def frame_range(self, rank) -> Tuple[int, int]:
+        o = offsets(self.frames)[rank]
+        return o, o + self.frames[rank]
+
+    def geo_rows(self) -> List[int]:
+        return [fr * self.P for fr in self.frames]
+
+    def geo_range(self, rank) -> Tuple[int, int]:
+        f0, f1 = self.frame_range(rank)
+        return f0 * self.P, f1 * self.P
+
+
+class SPContext:
+    """Per-process handle: rank / world, the process group, and the gather primitives used by the engine."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.layout: Optional[SPLayout] = None
+        self.n_gathers = 0
+        self.gather_bytes = 0
+
+    def set_grid(self, f, h, w):
+        if self.layout is None or (self.layout.f, self.layout.h, self.layout.w) != (f, h, w):
+            self.layout = SPLayout(self.world, f, h, w)
+        return self.layout
+
+    # ---- collectives ---------------------------------------------------------------------------------------------------
+    def all_gather_rows(self, x: torch.Tensor, sizes: List[int]) -> torch.Tensor:
+        """Concatenate the ranks' row blocks: x is this rank's [sizes[rank], C] block (contiguous); returns [sum(sizes), C].
+        Equal sizes: one all_gather_into_tensor.  Unequal (frame-aligned geometry shards): pad to the largest block, one
+        all_gather_into_tensor, then compact."""
+        assert x.is_contiguous() and x.shape[0] == sizes[self.rank]
+        C = x.shape[1:]
+        self.n_gathers += 1
+        if len(set(sizes)) == 1:
+            out = torch.empty((sum(sizes), *C), device=x.device, dtype=x.dtype)
+            dist.all_gather_into_tensor(out, x, group=self.group)
+            self.gather_bytes += out.numel() * out.element_size()
+            return out
+        m = max(sizes)
+        if x.shape[0] < m:
+            xp = torch.empty((m, *C), device=x.device, dtype=x.dtype)
+            xp[: x.shape[0]] = x
+            xp[x.shape[0]:] = 0
+        else:
+            xp = x
+        buf = torch.empty((self.world * m, *C), device=x.device, dtype=x.dtype)
+        dist.all_gather_into_tensor(buf, xp, group=self.group)
+        self.gather_bytes += buf.numel() * buf.element_size()
+        buf = buf.view(self.world, m, *C)
+        return torch.cat([buf[r, : sizes[r]] for r in range(self.world)], dim=0)
