@@ -207,3 +207,22 @@ def test_standalone_geometry_branch(model):
     finally:
         agg.global_blocks[0] = saved
         agg.aa_block_num = saved_n
+
+
+def test_pose_encoder_vs_reference_golden():
+    """CameraPoseEncoder (once per sample): Plücker rays [1,5,64,64,6] -> camera features [1, 32, 2048]."""
+    from FantasyWorld.diffsynth_wan21.models.pose_adaptor_ac3d import CameraPoseEncoder
+    from fwb200.synth import synth_init
+    g = gold("pose_encoder.pt")
+    enc = CameraPoseEncoder(context_dim=2048, in_channels=6, downscale_coef=8, pose_inject_method="adaln")
+    wrap = torch.nn.Module()
+    wrap.camera_condition = torch.nn.Module()
+    wrap.camera_condition.pose_encoder = enc
+    assert {k: list(v.shape) for k, v in wrap.state_dict().items()} == g["schema"]
+    synth_init(wrap, seed=0, gen_device="cpu")
+    enc = enc.to("cuda").to(torch.bfloat16).eval()
+    x = torch.randn(1, 5, 64, 64, 6, generator=torch.Generator().manual_seed(g["seed"]))
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y = enc(x.to("cuda", torch.bfloat16))
+    assert y.shape == g["out"].shape
+    assert rel_err(y.cpu(), g["out"]) < 3e-2, rel_err(y.cpu(), g["out"])
