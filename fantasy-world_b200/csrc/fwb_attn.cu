@@ -6,17 +6,19 @@
 //   F.scaled_dot_product_attention     FantasyWorld/vggt/layers/attention.py:61                     (VGGT frame / global)
 //
 // One CTA = 256 query rows (two 128-row Q tiles, ping-pong) x one (batch, head); it streams all KV tiles of 128 keys.
-//   warps 0-7    softmax for Q tile 0: warps 0-3 own columns 0..63 of the 128-key tile, warps 4-7 columns 64..127
-//                (thread <-> query row <-> TMEM lane; two threads per row exchange the row max through smem)
-//   warps 8-15   softmax for Q tile 1, same split
-//   warp  16     MMA issuer (one elected thread): S_i = Q_i K_j^T (SS), O_i += P_i V_j (TS: P read from TMEM)
-//   warp  17     TMA producer: Q once, K/V rings (SWIZZLE_128B boxes of 64 columns)
+//   warps 0-3   softmax for Q tile 0 (thread r <-> query row r <-> TMEM lane r)
+//   warps 4-7   softmax for Q tile 1
+//   warp  8     MMA issuer (one elected thread): S_i = Q_i K_j^T (SS), O_i += P_i V_j (TS: P read from TMEM)
+//   warp  9     TMA producer: Q once, K/V rings (SWIZZLE_128B boxes of 64 columns)
 // TMEM (512 columns): S_0 | S_1 (fp32 128 cols each; P_i (bf16) overwrites the first 64 columns of S_i) | O_0 | O_1.
 // Softmax: fp32, exp2 with the scale folded in, lazy rescaling of O (only when the row max grows by > 2^8),
 // P rounded to bf16 before PV — the same rounding point as flash-attn / cuDNN SDPA.
-// Why two threads per row: the ncu profile of the one-thread-per-row version (profiles/r01_attn_d128_v1.md) showed the
-// softmax warps waiting on S 37 % of the time while the tensor pipe was only 59 % active — the S -> softmax -> P -> PV
-// chain of a tile was latency-bound; halving the per-thread softmax work shortens that chain.
+// Hand-offs are fine-grained: P is written and signalled in four 32-key chunks, and the MMA warp issues the two PV
+// K-steps of a chunk as soon as it lands, so PV runs underneath the (MUFU-bound) exponential phase instead of after it.
+// (ncu, profiles/r01_attn_d128_v1.md: with whole-tile hand-offs the tensor pipe was 59 % active and the softmax warps
+// spent 37 % of their time waiting for S; the exponentials of a tile cost ~1024 clk of MUFU per SM sub-partition
+// whatever the thread count — splitting rows over two threads (v2) changed nothing — so the latency of each
+// S -> softmax -> P -> PV -> S hand-off is what has to be hidden.)
 // head_dim 96 (adapter) runs on the D=128 instance: TMA zero-fills columns 96..127 and QK^T skips the dead K-steps.
 // Roofline: tensor-pipe bound, 4*B*H*Lq*Lk*D FLOP.
 #include <math.h>
@@ -29,8 +31,7 @@ using namespace fwb;
 
 namespace {
 
-constexpr int kAttnThreads = 640;   // 16 softmax warps + MMA + TMA + 2 idle (register allocation is per 4 warps)
-constexpr int kWarpMma = 16, kWarpTma = 17;
+constexpr int kAttnThreads = 320;
 constexpr int BQ = 128;   // rows per Q tile
 constexpr int BKV = 128;  // keys per KV tile
 
@@ -78,10 +79,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sQ = smem;                                   // [2][kTileBytes]
   uint8_t* sK = smem + 2 * Cfg::kTileBytes;             // [ST][kTileBytes]
   uint8_t* sV = sK + ST * Cfg::kTileBytes;              // [ST][kTileBytes]
-  __shared__ uint64_t q_full[2], k_full[ST], k_empty[ST], v_full[ST], v_empty[ST], s_full[2], p_full[2], o_full[2];
+  __shared__ uint64_t q_full[2], k_full[ST], k_empty[ST], v_full[ST], v_empty[ST], s_full[2], p_chunk[2][4], o_full[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float xchg[2][2][BQ];   // [Q tile][column half][row]: partial row max of the current KV tile
-  __shared__ float xsum[2][2][BQ];   // partial row sums, exchanged once at the end
 
   const uint32_t warp = warp_id_uniform();
   const uint32_t lane = lane_id();
@@ -92,7 +91,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 8);  // one arrive per softmax warp of the tile
+      for (int c = 0; c < 4; ++c) mbar_init(&p_chunk[i][c], 4);  // one arrive per softmax warp per 32-key chunk of P
       mbar_init(&o_full[i], 1);
     }
     for (int s = 0; s < ST; ++s) {
@@ -106,7 +105,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
   }
-  if (warp == kWarpMma) {
+  if (warp == 8) {
     tmem_alloc(&tmem_base_s, 512);
     tmem_relinquish();
   }
@@ -115,7 +114,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == kWarpTma) {
+  if (warp == 9) {
     // ------------------------------------ TMA producer ------------------------------------
     if (elect_one()) {
       for (int i = 0; i < 2; ++i) {
@@ -136,7 +135,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tma_load_4d(sV + s * Cfg::kTileBytes + b * 16384, &tmV, &v_full[s], b * 64, head, j * BKV, batch);
       }
     }
-  } else if (warp == kWarpMma) {
+  } else if (warp == 8) {
     // ------------------------------------ MMA issuer --------------------------------------
     if (elect_one()) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);
@@ -153,16 +152,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                   idesc_qk, kk > 0);
         }
       };
-      auto issue_pv = [&](int i, uint32_t vs, bool acc) {
+      // PV for one 32-key chunk of P (two K=16 steps).  16 kv rows per step = 2048 B of the V tile;
+      // LBO = stride between the 64-column d boxes, SBO = 8 kv rows.
+      auto issue_pv_chunk = [&](int i, uint32_t vs, int c, bool acc) {
         const uint32_t va = v_addr + vs * Cfg::kTileBytes;
         const uint32_t d_tmem = tmem_base + Cfg::kColO + i * D;
         const uint32_t a_tmem = tmem_base + Cfg::kColS + i * 128;
 #pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk) {
-          // 16 kv rows per step = 2048 B; LBO = stride between the 64-column d boxes, SBO = 8 kv rows
-          umma_ts(d_tmem, a_tmem + kk * 8, make_smem_desc(va + kk * 2048, 16384, 1024, SWZ_128B), idesc_pv,
-                  acc || kk > 0);
-        }
+        for (int kk = 2 * c; kk < 2 * c + 2; ++kk)
+          umma_ts(d_tmem, a_tmem + kk * 8, make_smem_desc(va + kk * 2048, 16384, 1024, SWZ_128B), idesc_pv, acc || kk > 0);
       };
 
       mbar_wait(&q_full[0], 0);
@@ -179,10 +177,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int j = 0; j < n_kv; ++j) {
         const uint32_t vs = j % ST, vph = (j / ST) & 1;
         for (int i = 0; i < 2; ++i) {
-          mbar_wait(&p_full[i], j & 1);
           if (i == 0) mbar_wait(&v_full[vs], vph);
-          tc_fence_after();
-          issue_pv(i, vs, j > 0);
+          for (int c = 0; c < 4; ++c) {
+            mbar_wait(&p_chunk[i][c], j & 1);
+            tc_fence_after();
+            issue_pv_chunk(i, vs, c, j > 0);
+          }
           if (i == 1) tc_commit(&v_empty[vs]);
           if (j + 1 < n_kv) {
             const uint32_t ks = (j + 1) % ST, kph = ((j + 1) / ST) & 1;
@@ -199,47 +199,44 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-  } else if (warp < 16) {
+  } else {
     // ------------------------------------ softmax + epilogue ------------------------------
-    const int i = warp >> 3;                 // Q tile handled by this pair of warpgroups
-    const uint32_t half = (warp >> 2) & 1;   // which 64 of the 128 key columns this thread owns
+    const int i = warp >> 2;                 // Q tile handled by this warpgroup
     const uint32_t quad = warp & 3;          // TMEM lane quadrant
     const uint32_t lane_off = (quad * 32) << 16;
-    const uint32_t rloc = quad * 32 + lane;  // row inside the Q tile
     const uint32_t s_tmem = tmem_base + Cfg::kColS + i * 128 + lane_off;
-    const uint32_t o_tmem = tmem_base + Cfg::kColO + i * D + half * (D / 2) + lane_off;
+    const uint32_t o_tmem = tmem_base + Cfg::kColO + i * D + lane_off;
     const float sl2 = p.scale_log2;
-    float m_used = -INFINITY;  // running (stale-tolerant) row max in scaled log2 units; identical in both threads of a row
-    float l_sum = 0.f;         // partial row sum over this thread's columns
+    float m_used = -INFINITY;  // running (stale-tolerant) row max in scaled log2 units
+    float l_sum = 0.f;
 
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[i], j & 1);
       tc_fence_after();
-      uint32_t v[64];
-      tmem_ld32(s_tmem + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-      tmem_ld32(s_tmem + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+      uint32_t v[128];
+      tmem_ld32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tmem_ld32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+      tmem_ld32(s_tmem + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
+      tmem_ld32(s_tmem + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
       tmem_ld_wait();
 
       if (j == n_kv - 1) {
-        const int valid = p.Lk - j * BKV - (int)half * 64;   // valid columns among this thread's 64
-        if (valid < 64) {
+        const int valid = p.Lk - j * BKV;
+        if (valid < BKV) {
 #pragma unroll
-          for (int c = 0; c < 64; ++c)
+          for (int c = 0; c < 128; ++c)
             if (c >= valid) v[c] = 0xFF800000u;  // -inf
         }
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 64; c += 4) {
+      for (int c = 0; c < 128; c += 4) {
         mx0 = fmaxf(mx0, __uint_as_float(v[c]));
         mx1 = fmaxf(mx1, __uint_as_float(v[c + 1]));
         mx2 = fmaxf(mx2, __uint_as_float(v[c + 2]));
         mx3 = fmaxf(mx3, __uint_as_float(v[c + 3]));
       }
-      const float pm = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      xchg[i][half][rloc] = pm;
-      asm volatile("bar.sync %0, 256;" ::"r"(1 + i) : "memory");   // the 8 warps of this Q tile
-      const float m_new = fmaxf(pm, xchg[i][half ^ 1][rloc]) * sl2;
+      const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
       const bool need = m_new > m_used + 8.0f;
       if (__any_sync(0xffffffffu, need)) {
         const float m_next = fmaxf(m_used, m_new);
@@ -247,10 +244,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         l_sum *= alpha;
         m_used = m_next;
         if (j > 0) {
-          // rescale this thread's half of the O row.  PV_i(j-1) has completed: it was issued before S_i(j), whose
-          // commit we waited on.
+          // rescale this row of O.  PV_i(j-1) has completed: it was issued before S_i(j), whose commit we waited on.
 #pragma unroll
-          for (int c0 = 0; c0 < D / 2; c0 += 16) {
+          for (int c0 = 0; c0 < D; c0 += 16) {
             uint32_t o[16];
             tmem_ld16(o_tmem + c0, o);
             tmem_ld_wait();
@@ -260,44 +256,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       }
+      // the O rescale above (if any) must be visible before the first PV of this tile is issued
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      uint32_t pk[32];
 #pragma unroll
-      for (int c = 0; c < 64; c += 4) {
-        const float x0 = fmaf(__uint_as_float(v[c]), sl2, -m_used);
-        const float x1 = fmaf(__uint_as_float(v[c + 1]), sl2, -m_used);
-        const float x2 = fmaf(__uint_as_float(v[c + 2]), sl2, -m_used);
-        const float x3 = fmaf(__uint_as_float(v[c + 3]), sl2, -m_used);
-        const float p0 = fast_exp2(x0);
-        const float p1 = fast_exp2(x1);
-        const float p2 = fast_exp2(x2);
-        const float p3 = (EMU >= 1) ? exp2_poly(x3) : fast_exp2(x3);
-        a0 += p0; a1 += p1; a2 += p2; a3 += p3;
-        pk[c / 2] = pack_bf16x2(p0, p1);
-        pk[c / 2 + 1] = pack_bf16x2(p2, p3);
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 32 * ch; c < 32 * ch + 32; c += 4) {
+          const float x0 = fmaf(__uint_as_float(v[c]), sl2, -m_used);
+          const float x1 = fmaf(__uint_as_float(v[c + 1]), sl2, -m_used);
+          const float x2 = fmaf(__uint_as_float(v[c + 2]), sl2, -m_used);
+          const float x3 = fmaf(__uint_as_float(v[c + 3]), sl2, -m_used);
+          const float p0 = fast_exp2(x0);
+          const float p1 = fast_exp2(x1);
+          const float p2 = fast_exp2(x2);
+          const float p3 = (EMU >= 1) ? exp2_poly(x3) : fast_exp2(x3);
+          a0 += p0; a1 += p1; a2 += p2; a3 += p3;
+          pk[(c - 32 * ch) / 2] = pack_bf16x2(p0, p1);
+          pk[(c - 32 * ch) / 2 + 1] = pack_bf16x2(p2, p3);
+        }
+        tmem_st16(s_tmem + 16 * ch, pk);   // P chunk: keys 32ch..32ch+31 as bf16 pairs in columns [16ch, 16ch+16)
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_chunk[i][ch]);
       }
       l_sum += (a0 + a1) + (a2 + a3);
-      tmem_st32(s_tmem + half * 32, pk);   // P (bf16 pairs) occupies columns [0, 64) of the S region
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[i]);
     }
 
-    // epilogue: O / l  -> bf16 -> global.  Row sum = sum of the two threads' partial sums.
-    xsum[i][half][rloc] = l_sum;
-    asm volatile("bar.sync %0, 256;" ::"r"(1 + i) : "memory");
-    const float inv_l = 1.f / (l_sum + xsum[i][half ^ 1][rloc]);
+    // epilogue: O / l  -> bf16 -> global
     mbar_wait(&o_full[i], 0);
     tc_fence_after();
-    const int row = (qblock * 2 + i) * BQ + rloc;
-    __nv_bfloat16* orow = p.out + (long long)batch * p.o_sb + (long long)row * p.o_sl + (long long)head * p.o_sh + half * (D / 2);
+    const int row = (qblock * 2 + i) * BQ + quad * 32 + lane;
+    const float inv_l = 1.f / l_sum;
+    __nv_bfloat16* orow = p.out + (long long)batch * p.o_sb + (long long)row * p.o_sl + (long long)head * p.o_sh;
 #pragma unroll
-    for (int c0 = 0; c0 < D / 2; c0 += 32) {
+    for (int c0 = 0; c0 < D; c0 += 32) {
       uint32_t o[32];
       tmem_ld32(o_tmem + c0, o);
       tmem_ld_wait();
-      if (row < p.Lq && (int)(half * (D / 2)) + c0 < p.d_real) {
+      if (row < p.Lq && c0 < p.d_real) {
 #pragma unroll
         for (int c = 0; c < 32; c += 8) {
           float y[8];
@@ -325,7 +323,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kWarpMma) tmem_dealloc(tmem_base, 512);
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
 int make_qkv_map(CUtensorMap* m, const fwb_tensor4_t* t, int B, int H, int L, int D) {
