@@ -13,12 +13,10 @@
 // TMEM (512 columns): S_0 | S_1 (fp32 128 cols each; P_i (bf16) overwrites the first 64 columns of S_i) | O_0 | O_1.
 // Softmax: fp32, exp2 with the scale folded in, lazy rescaling of O (only when the row max grows by > 2^8),
 // P rounded to bf16 before PV — the same rounding point as flash-attn / cuDNN SDPA.
-// Hand-offs are fine-grained: P is written and signalled in four 32-key chunks, and the MMA warp issues the two PV
-// K-steps of a chunk as soon as it lands, so PV runs underneath the (MUFU-bound) exponential phase instead of after it.
-// (ncu, profiles/r01_attn_d128_v1.md: with whole-tile hand-offs the tensor pipe was 59 % active and the softmax warps
-// spent 37 % of their time waiting for S; the exponentials of a tile cost ~1024 clk of MUFU per SM sub-partition
-// whatever the thread count — splitting rows over two threads (v2) changed nothing — so the latency of each
-// S -> softmax -> P -> PV -> S hand-off is what has to be hidden.)
+// Variants measured on B200 and NOT kept (profiles/r01_attention_variants.md): two softmax threads per row (v2, same speed:
+// the exponentials of a tile cost ~1024 clk of MUFU per SM sub-partition whatever the thread count), P handed over in
+// four 32-key chunks (v3, slower: four mbarrier wake-ups per tile on the MMA thread cost more than the overlap buys),
+// FMA-pipe exp2 polynomial for 25-75 % of the elements (slower: the softmax warps are issue/latency bound, not MUFU bound).
 // head_dim 96 (adapter) runs on the D=128 instance: TMA zero-fills columns 96..127 and QK^T skips the dead K-steps.
 // Roofline: tensor-pipe bound, 4*B*H*Lq*Lk*D FLOP.
 #include <math.h>
@@ -79,7 +77,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sQ = smem;                                   // [2][kTileBytes]
   uint8_t* sK = smem + 2 * Cfg::kTileBytes;             // [ST][kTileBytes]
   uint8_t* sV = sK + ST * Cfg::kTileBytes;              // [ST][kTileBytes]
-  __shared__ uint64_t q_full[2], k_full[ST], k_empty[ST], v_full[ST], v_empty[ST], s_full[2], p_chunk[2][4], o_full[2];
+  __shared__ uint64_t q_full[2], k_full[ST], k_empty[ST], v_full[ST], v_empty[ST], s_full[2], p_full[2], o_full[2];
   __shared__ uint32_t tmem_base_s;
 
   const uint32_t warp = warp_id_uniform();
@@ -91,7 +89,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&s_full[i], 1);
-      for (int c = 0; c < 4; ++c) mbar_init(&p_chunk[i][c], 4);  // one arrive per softmax warp per 32-key chunk of P
+      mbar_init(&p_full[i], 4);  // one arrive per softmax warp
       mbar_init(&o_full[i], 1);
     }
     for (int s = 0; s < ST; ++s) {
@@ -152,15 +150,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                   idesc_qk, kk > 0);
         }
       };
-      // PV for one 32-key chunk of P (two K=16 steps).  16 kv rows per step = 2048 B of the V tile;
-      // LBO = stride between the 64-column d boxes, SBO = 8 kv rows.
-      auto issue_pv_chunk = [&](int i, uint32_t vs, int c, bool acc) {
+      auto issue_pv = [&](int i, uint32_t vs, bool acc) {
         const uint32_t va = v_addr + vs * Cfg::kTileBytes;
         const uint32_t d_tmem = tmem_base + Cfg::kColO + i * D;
         const uint32_t a_tmem = tmem_base + Cfg::kColS + i * 128;
 #pragma unroll
-        for (int kk = 2 * c; kk < 2 * c + 2; ++kk)
-          umma_ts(d_tmem, a_tmem + kk * 8, make_smem_desc(va + kk * 2048, 16384, 1024, SWZ_128B), idesc_pv, acc || kk > 0);
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          // 16 kv rows per step = 2048 B; LBO = stride between the 64-column d boxes, SBO = 8 kv rows
+          umma_ts(d_tmem, a_tmem + kk * 8, make_smem_desc(va + kk * 2048, 16384, 1024, SWZ_128B), idesc_pv,
+                  acc || kk > 0);
+        }
       };
 
       mbar_wait(&q_full[0], 0);
@@ -177,12 +176,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int j = 0; j < n_kv; ++j) {
         const uint32_t vs = j % ST, vph = (j / ST) & 1;
         for (int i = 0; i < 2; ++i) {
+          mbar_wait(&p_full[i], j & 1);
           if (i == 0) mbar_wait(&v_full[vs], vph);
-          for (int c = 0; c < 4; ++c) {
-            mbar_wait(&p_chunk[i][c], j & 1);
-            tc_fence_after();
-            issue_pv_chunk(i, vs, c, j > 0);
-          }
+          tc_fence_after();
+          issue_pv(i, vs, j > 0);
           if (i == 1) tc_commit(&v_empty[vs]);
           if (j + 1 < n_kv) {
             const uint32_t ks = (j + 1) % ST, kph = ((j + 1) / ST) & 1;
@@ -256,32 +253,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       }
-      // the O rescale above (if any) must be visible before the first PV of this tile is issued
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      uint32_t pk[64];
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int c = 32 * ch; c < 32 * ch + 32; c += 4) {
-          const float x0 = fmaf(__uint_as_float(v[c]), sl2, -m_used);
-          const float x1 = fmaf(__uint_as_float(v[c + 1]), sl2, -m_used);
-          const float x2 = fmaf(__uint_as_float(v[c + 2]), sl2, -m_used);
-          const float x3 = fmaf(__uint_as_float(v[c + 3]), sl2, -m_used);
-          const float p0 = fast_exp2(x0);
-          const float p1 = fast_exp2(x1);
-          const float p2 = fast_exp2(x2);
-          const float p3 = (EMU >= 1) ? exp2_poly(x3) : fast_exp2(x3);
-          a0 += p0; a1 += p1; a2 += p2; a3 += p3;
-          pk[(c - 32 * ch) / 2] = pack_bf16x2(p0, p1);
-          pk[(c - 32 * ch) / 2 + 1] = pack_bf16x2(p2, p3);
-        }
-        tmem_st16(s_tmem + 16 * ch, pk);   // P chunk: keys 32ch..32ch+31 as bf16 pairs in columns [16ch, 16ch+16)
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_chunk[i][ch]);
+      for (int c = 0; c < 128; c += 4) {
+        const float x0 = fmaf(__uint_as_float(v[c]), sl2, -m_used);
+        const float x1 = fmaf(__uint_as_float(v[c + 1]), sl2, -m_used);
+        const float x2 = fmaf(__uint_as_float(v[c + 2]), sl2, -m_used);
+        const float x3 = fmaf(__uint_as_float(v[c + 3]), sl2, -m_used);
+        const float p0 = fast_exp2(x0);
+        const float p1 = fast_exp2(x1);
+        const float p2 = fast_exp2(x2);
+        const float p3 = (EMU >= 1) ? exp2_poly(x3) : fast_exp2(x3);
+        a0 += p0; a1 += p1; a2 += p2; a3 += p3;
+        pk[c / 2] = pack_bf16x2(p0, p1);
+        pk[c / 2 + 1] = pack_bf16x2(p2, p3);
       }
       l_sum += (a0 + a1) + (a2 + a3);
+      tmem_st32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+      tmem_st32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[i]);
     }
 
     // epilogue: O / l  -> bf16 -> global
