@@ -23,6 +23,7 @@ from ..diffsynth_wan21 import ModelManager, WanVideoPipeline
 from ..diffsynth_wan21.models.camera_control import CameraConditionModel
 from ..diffsynth_wan21.models.wan_video_dit import (build_freqs_3d_with_extra_cis, precompute_freqs_cis_3d,
                                                     sinusoidal_embedding_1d, _grid_freqs)
+from ..fusion.core import FusionCore
 from ..fusion.layer.block import IRGBlock
 from ..vggt.models.vggt import VGGT
 
@@ -32,7 +33,7 @@ LATENT_STD = [2.8184, 1.4541, 2.3275, 2.6558, 1.2196, 1.7708, 2.6052, 2.0743,
               3.2687, 2.1526, 2.8652, 1.5579, 1.6382, 1.1253, 2.8251, 1.9160]
 
 
-class FantasyWorldFusionModel(nn.Module):
+class FantasyWorldFusionModel(FusionCore):
     def __init__(self, start_index: int = 16, use_gradient_checkpointing: bool = True,
                  use_gradient_checkpointing_offload: bool = False, cross_attention_list: list = [0], dit_path=None,
                  vggt_cfg: dict | None = None, camera_control: bool = False, camera_cfg: dict | None = None,
@@ -73,166 +74,18 @@ class FantasyWorldFusionModel(nn.Module):
         self.to(torch.bfloat16)
 
     # ------------------------------------------------------------------------------------------------------------------
-    # loop-invariant inputs
-    # ------------------------------------------------------------------------------------------------------------------
-    def embed_context(self, context, clip_feature):
-        """text_embedding(context) and img_emb(clip) depend only on the prompt / first frame: computed once per
-        (context, clip) tensor pair instead of once per forward.  ref: model_wan21.py:123-128."""
-        from fwb200.engine import IdCache
-        dit = self.pipe.dit
-        cache = self.__dict__.get("_fwb_ctx")
-        if cache is None:
-            cache = self.__dict__["_fwb_ctx"] = IdCache(4)
-
-        def build():
-            ctx = dit.embed_text(context)
-            if dit.has_image_input:
-                ctx = torch.cat([dit.img_emb(clip_feature).to(ctx.dtype), ctx], dim=1)
-            return ctx.contiguous()
-
-        srcs = (context,) + ((clip_feature,) if clip_feature is not None else ()) + (dit.text_embedding[0].weight,)
-        return cache.get(srcs, None, build)
-
-    def rope_tables(self, f, h, w, device):
-        """freqs (D=128), freqs_bi_dit (D=96), freqs_bi_agg (D=96 with 5 identity rotations per frame).
-        ref: model_wan21.py:132-147."""
-        def build():
-            dit = self.pipe.dit
-            freqs = _grid_freqs(dit.freqs, f, h, w).reshape(f * h * w, 1, -1).to(device)
-            bi_dit = _grid_freqs(self.freqs_bicross, f, h, w).reshape(f * h * w, 1, -1).to(device)
-            bi_agg = build_freqs_3d_with_extra_cis(self.freqs_bicross, f, h, w, n_extra=5, device=device)
-            return freqs, bi_dit, bi_agg
-
-        store = self.__dict__.setdefault("_fwb_rope", {})
-        key = (f, h, w, str(device))
-        if key not in store:
-            store[key] = build()
-        return store[key]
-
-    # ------------------------------------------------------------------------------------------------------------------
     def joint_forward(self, x: torch.Tensor, timestep: torch.Tensor, context: torch.Tensor,
                       clip_feature: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None,
                       use_gradient_checkpointing: bool = True, camera_token=None, plucker_fea: Optional[torch.Tensor] = None,
                       plucker_context_lens: Optional[torch.Tensor] = None, uncond=False, return_prediction=False, **kwargs):
-        """One denoiser evaluation.  ref: model_wan21.py:104-224.  With `self.sp` set (fwb200.sp.SPContext) the tokens are
-        sharded over the ranks of that group (see _joint_forward_sp); inputs and outputs are replicated either way."""
+        """One denoiser evaluation.  ref: model_wan21.py:104-224.  With `self.sp` set (fwb200.sp.SPContext, world > 1) the
+        tokens are sharded over the ranks of that group; inputs and outputs are replicated either way."""
         ops.require_device()
-        if getattr(self, "sp", None) is not None and self.sp.world > 1:
-            return self._joint_forward_sp(x, timestep, context, clip_feature, y, camera_token, plucker_fea, plucker_context_lens,
-                                          uncond, return_prediction)
-        dit, vggt, agg = self.pipe.dit, self.vggt, self.vggt.aggregator
-        t, t_mod = dit.embed_time(timestep)
         ctx = self.embed_context(context, clip_feature)
-        if dit.has_image_input:
+        if self.pipe.dit.has_image_input:
             x = torch.cat([x, y], dim=1)
-        x, (f, h, w) = dit.patchify(x)
-        freqs, freqs_bi_dit, freqs_bi_agg = self.rope_tables(f, h, w, x.device)
-        kw = dict(plucker_fea=plucker_fea, plucker_context_lens=plucker_context_lens)
-
-        for i in range(self.start_index):                                   # Preconditioning Blocks
-            x = dit.blocks[i](x, ctx, t_mod, freqs, **kw)
-
-        B = x.shape[0]
-        patch_token = vggt.project_tokens(x).view(B, f, h, w, -1)           # 5120 -> 1024 per token
-        e0 = vggt.time_modulation(timestep)
-        tokens, pos = agg._process_aggregator_input(patch_token, camera_token)
-        S, (_, P, C) = f, tokens.shape
-
-        frame_idx = global_idx = 0
-        output_list = []
-        for i in range(len(dit.blocks) - self.start_index):
-            tokens, frame_idx, frame_inter = agg._process_frame_attention(tokens, B, S, P, C, frame_idx, pos=pos, e0=e0)
-            if i in self.cross_attention_list:
-                x, tokens, global_inter = self.IRGBlock[i](x_dit=x, x_agg=tokens, context=ctx, t_mod=t_mod, freqs=freqs,
-                                                           freqs_dit=freqs_bi_dit, freqs_agg=freqs_bi_agg, pos=pos, e0=e0,
-                                                           uncond=uncond, **kw)
-                global_idx += 1
-            else:
-                x = dit.blocks[i + self.start_index](x, ctx, t_mod, freqs, **kw)
-                tokens, global_idx, global_inter = agg._process_global_attention(tokens, B, S, P, C, global_idx, pos=pos, e0=e0)
-            if return_prediction:  # only the last step consumes these 2C-wide intermediates (ref: :208-212, :217-222)
-                output_list.extend(torch.cat([a, b], dim=-1) for a, b in zip(frame_inter, global_inter))
-
-        x = dit.unpatchify(dit.head(x, t), (f, h, w))
-        if return_prediction:
-            return x, vggt._head_predction(patch_token, agg.patch_start_idx, output_list)
-        return x, None
-
-    # ------------------------------------------------------------------------------------------------------------------
-    def _local_rows(self, t: torch.Tensor, r0: int, r1: int):
-        """Cached row slice t[:, r0:r1] of a loop-invariant [1, L, C] tensor (stable identity keeps downstream caches warm)."""
-        from fwb200.engine import IdCache
-        cache = self.__dict__.get("_fwb_rows")
-        if cache is None:
-            cache = self.__dict__["_fwb_rows"] = IdCache(4)
-        return cache.get((t,), (r0, r1), lambda: t[:, r0:r1].contiguous())
-
-    def _joint_forward_sp(self, x, timestep, context, clip_feature, y, camera_token, plucker_fea, plucker_context_lens, uncond,
-                          return_prediction):
-        """Sequence-parallel joint_forward.  Video tokens: contiguous L/P rows per rank.  Geometry tokens:
-        frame-aligned shards.  Collectives per forward: one all-gather of packed K|V per attention (40 DiT self-attentions,
-        24 VGGT global attentions, 2 x 24 adapter directions), one gather of the 1024-wide projected tokens, one gather of the
-        64-wide head output.  Weights are replicated."""
-        import fwb200.engine as E
-        sp = self.sp
-        dit, vggt, agg = self.pipe.dit, self.vggt, self.vggt.aggregator
-        assert camera_token is None, "camera_token conditioning is not sharded (not used by the sampler)"
-        t, t_mod = dit.embed_time(timestep)
-        ctx = self.embed_context(context, clip_feature)
-        if dit.has_image_input:
-            x = torch.cat([x, y], dim=1)
-        b, cin, F_, H_, W_ = x.shape
-        pf, ph, pw = dit.patch_size
-        f, h, w = F_ // pf, H_ // ph, W_ // pw
-        lay = sp.set_grid(f, h, w)
-        r0, r1 = lay.video_range(sp.rank)
-        f0, f1 = lay.frame_range(sp.rank)
-        # patchify only this rank's rows of the (f h w) token grid
-        cols = E.as_bf16(x).view(b, cin, f, pf, h, ph, w, pw).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(f * h * w, cin * pf * ph * pw)
-        xl = E.lin(cols[r0:r1].contiguous(), dit.patch_embedding, round_flags=ops.ROUND_AFTER_BIAS).unsqueeze(0)
-        freqs, freqs_bi_dit, freqs_bi_agg = self.rope_tables(f, h, w, xl.device)
-        kw = dict(plucker_fea=self._local_rows(plucker_fea, r0, r1) if plucker_fea is not None else None,
-                  plucker_context_lens=plucker_context_lens)
-        E.SP = sp
-        try:
-            for i in range(self.start_index):
-                xl = dit.blocks[i](xl, ctx, t_mod, freqs, **kw)
-            # 5120 -> 1024 projection on local rows, then one gather so that every rank can pick its frames
-            proj = sp.all_gather_rows(vggt.project_tokens(xl)[0], lay.video_rows)              # [L, 1024]
-            patch_local = proj.view(f, h, w, -1)[f0:f1].unsqueeze(0)                            # [1, f_loc, h, w, 1024]
-            e0 = vggt.time_modulation(timestep)
-            tokens, pos = agg._process_aggregator_input(patch_local, None, frame_range=(f0, f1))
-            S, (_, P, C) = f1 - f0, tokens.shape
-            frame_idx = global_idx = 0
-            keep = None
-            if return_prediction:
-                n_layers = len(dit.blocks) - self.start_index
-                keep = {n_layers - 1}
-                for head in (vggt.depth_head, vggt.point_head):
-                    if head is not None:
-                        keep |= {li % n_layers for li in head.intermediate_layer_idx}
-            output_list = []
-            for i in range(len(dit.blocks) - self.start_index):
-                tokens, frame_idx, frame_inter = agg._process_frame_attention(tokens, 1, S, P, C, frame_idx, pos=pos, e0=e0)
-                assert i in self.cross_attention_list, "sequence parallel path expects every post-PCB block to be an IRG block"
-                xl, tokens, global_inter = self.IRGBlock[i](x_dit=xl, x_agg=tokens, context=ctx, t_mod=t_mod, freqs=freqs,
-                                                            freqs_dit=freqs_bi_dit, freqs_agg=freqs_bi_agg, pos=pos, e0=e0,
-                                                            uncond=uncond, **kw)
-                global_idx += 1
-                if return_prediction:
-                    if i in keep:   # gather the [rows, 2C] intermediates the heads read; the others are never touched
-                        loc = torch.cat([frame_inter[0].reshape(S * P, C), global_inter[0].reshape(S * P, C)], dim=-1).contiguous()
-                        output_list.append(sp.all_gather_rows(loc, lay.geo_rows()).view(1, f, P, 2 * C))
-                    else:
-                        output_list.append(None)
-            out_local = dit.head(xl, t)[0]                                                       # [L/P, 64]
-        finally:
-            E.SP = None
-        out = dit.unpatchify(sp.all_gather_rows(out_local.contiguous(), lay.video_rows).unsqueeze(0), (f, h, w))
-        if return_prediction:
-            patch_token = proj.view(1, f, h, w, -1)
-            return out, vggt._head_predction(patch_token, agg.patch_start_idx, output_list)
-        return out, None
+        return self._joint_core(x, timestep, ctx, dict(plucker_context_lens=plucker_context_lens), plucker_fea=plucker_fea,
+                                camera_token=camera_token, uncond=uncond, return_prediction=return_prediction)
 
     # ------------------------------------------------------------------------------------------------------------------
     @torch.no_grad()

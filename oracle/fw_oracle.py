@@ -179,17 +179,20 @@ def dit_self_attn(sd, pfx, x, rope_tab, nm=FP32):
 
 def dit_cross_attn(sd, pfx, x, context, plucker_fea, nm=FP32):
     """CrossAttentionProcessor / CrossAttentionAdapterProcessor('adaln') —
-    wan_video_dit.py:185-201, camera_control.py:92-148.  context = [clip(257) | text]."""
-    img, ctx = context[:, :257], context[:, 257:]
+    wan_video_dit.py:185-201, camera_control.py:92-148.  context = [clip(257) | text] when the block has image input
+    (Wan2.1-I2V: k_img / v_img weights present), else text only (Wan2.2-Fun, diffsynth_wan22/models/wan_video_dit.py:203-223)."""
+    has_img = (pfx + ".k_img.weight") in sd
+    img, ctx = (context[:, :257], context[:, 257:]) if has_img else (None, context)
     q = rms_norm(linear(sd, pfx + ".q", x, nm), sd[pfx + ".norm_q.weight"], 1e-6, nm)
     k = rms_norm(linear(sd, pfx + ".k", ctx, nm), sd[pfx + ".norm_k.weight"], 1e-6, nm)
     v = linear(sd, pfx + ".v", ctx, nm)
     qh = heads_split(q, DIT_HEADS)
     o = heads_merge(sdpa(qh, heads_split(k, DIT_HEADS), heads_split(v, DIT_HEADS), nm))
-    k_img = rms_norm(linear(sd, pfx + ".k_img", img, nm), sd[pfx + ".norm_k_img.weight"], 1e-6, nm)
-    v_img = linear(sd, pfx + ".v_img", img, nm)
-    o_img = heads_merge(sdpa(qh, heads_split(k_img, DIT_HEADS), heads_split(v_img, DIT_HEADS), nm))
-    o = nm.r(o + o_img)
+    if has_img:
+        k_img = rms_norm(linear(sd, pfx + ".k_img", img, nm), sd[pfx + ".norm_k_img.weight"], 1e-6, nm)
+        v_img = linear(sd, pfx + ".v_img", img, nm)
+        o_img = heads_merge(sdpa(qh, heads_split(k_img, DIT_HEADS), heads_split(v_img, DIT_HEADS), nm))
+        o = nm.r(o + o_img)
     has_adapter = (pfx + ".processor.k_proj.group1.weight") in sd
     if has_adapter and plucker_fea is not None and not bool(torch.all(plucker_fea == 0)):
         # GroupLinearDualK (camera_control.py:24-39), GroupLinearDualV (:42-63): scale is the float 0.0
@@ -412,16 +415,34 @@ def aggregator_input(sd, pfx, patch_token):
 # ------------------------------------------------------------------------------------------------------------------
 # joint_forward (without the geometry heads) and the sampler step
 # ------------------------------------------------------------------------------------------------------------------
+def control_adapter(sd, pfx, control, nm=FP32):
+    """SimpleAdapter — diffsynth_wan22/models/wan_video_camera_controller.py:8-47, 64-76: PixelUnshuffle(8) ->
+    Conv2d(k = s = 2) -> x + conv2(relu(conv1(x))); frames folded into the batch.  Returns tokens [1, f*h*w, dim]."""
+    b, c, f, H, W = control.shape
+    z = F.pixel_unshuffle(control.permute(0, 2, 1, 3, 4).reshape(b * f, c, H, W), 8)
+    p = pfx + ".control_adapter"
+    z = nm.r(F.conv2d(nm.r(z), nm.r(sd[p + ".conv.weight"].float()), nm.r(sd[p + ".conv.bias"].float()), stride=2))
+    r = p + ".residual_blocks.0"
+    h1 = nm.r(F.relu(nm.r(F.conv2d(z, nm.r(sd[r + ".conv1.weight"].float()), nm.r(sd[r + ".conv1.bias"].float()), padding=1))))
+    z = nm.r(z + nm.r(F.conv2d(h1, nm.r(sd[r + ".conv2.weight"].float()), nm.r(sd[r + ".conv2.bias"].float()), padding=1)))
+    return z.view(b, f, *z.shape[1:]).permute(0, 1, 3, 4, 2).reshape(b, -1, z.shape[1])
+
+
 def joint_forward(sd, x, timestep, context, clip_feature, y, plucker_fea, start_index, n_irg, nm=FP32,
-                  collect_intermediates=False):
-    """FantasyWorldFusionModel.joint_forward — fusion/model_wan21.py:104-224 (heads excluded).
-    Returns the predicted latent [1,16,f,H,W] and, optionally, the per-layer [B,S,P,2C] intermediates."""
+                  collect_intermediates=False, control=None):
+    """FantasyWorldFusionModel.joint_forward — fusion/model_wan21.py:104-224 (heads excluded); with clip_feature=None and
+    `control` given it is the Wan2.2 variant, fusion/model_wan22.py:226-348 (no CLIP context, control adapter added to the
+    patch embedding, no camera AdaLN).  Returns the predicted latent [1,16,f,H,W] and, optionally, the per-layer
+    [B,S,P,2C] intermediates."""
     dit = "pipe.dit"
     t, t_mod = dit_time_embed(sd, dit, timestep, nm)
     ctx = text_embed(sd, dit, context, nm)
     x = torch.cat([x, y], dim=1)
-    ctx = torch.cat([nm.r(img_embed(sd, dit, clip_feature, nm)), ctx], dim=1)
+    if clip_feature is not None:
+        ctx = torch.cat([nm.r(img_embed(sd, dit, clip_feature, nm)), ctx], dim=1)
     x, (f, h, w) = patchify(sd, dit, x, nm)
+    if control is not None:
+        x = nm.r(x + control_adapter(sd, dit, control, nm))
     tab = rope_table_3d(128, f, h, w)
     tab_bi_dit = rope_table_3d(96, f, h, w)
     tab_bi_agg = rope_table_3d_with_extra(96, f, h, w, 5)

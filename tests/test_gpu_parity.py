@@ -226,3 +226,39 @@ def test_pose_encoder_vs_reference_golden():
         y = enc(x.to("cuda", torch.bfloat16))
     assert y.shape == g["out"].shape
     assert rel_err(y.cpu(), g["out"]) < 3e-2, rel_err(y.cpu(), g["out"])
+
+
+def test_wan22_joint_forward_vs_reference_golden(fp32_rope_angles):
+    """Wan2.2-Fun-A14B-Control-Camera fusion model (BASELINE config 4 family), reduced depth, GPU vs the reference golden."""
+    import json
+    import torch.nn as nn
+    from _common import GOLD
+    from FantasyWorld.diffsynth_wan22.models.wan_video_dit import WAN22_FUN_A14B_CONTROL_CAMERA
+    from FantasyWorld.fusion.model_wan22 import FantasyWorldFusionModel as Fusion22
+    from FantasyWorld.diffsynth_wan21.models.wan_video_dit import precompute_freqs_cis_3d
+    from fwb200.synth import VGGT_CFG, materialize, synth_init, synth_inputs
+    g = gold("joint_forward_wan22.pt")
+    schema = json.loads((GOLD / "schema_wan22_reduced.json").read_text())
+    with torch.device("meta"):
+        m = Fusion22(start_index=1, use_gradient_checkpointing=False, cross_attention_list=[0], dit_path=None, lora_path=None,
+                     vggt_cfg=dict(VGGT_CFG, enable_camera=False, enable_depth=False, enable_point=False), camera_control=True,
+                     camera_cfg=dict(use_info="plucker"), dit_config=dict(WAN22_FUN_A14B_CONTROL_CAMERA, num_layers=2))
+    agg = m.vggt.aggregator
+    agg.frame_blocks = nn.ModuleList(list(agg.frame_blocks)[:1])
+    agg.global_blocks = nn.ModuleList(list(agg.global_blocks)[:1])
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == schema      # same keys as the reference's Wan2.2 model
+    materialize(m, "cuda", torch.bfloat16)
+    m.pipe.dit.freqs = precompute_freqs_cis_3d(128)
+    m.freqs_bicross = precompute_freqs_cis_3d(96)
+    synth_init(m, seed=0, gen_device="cpu")
+    m.eval()
+    f, h, w = g["grid"]
+    inp = synth_inputs(f, h, w, device="cuda", seed=1024, text_len=g["text_len"])
+    control = torch.randn(1, 24, f, 16 * h, 16 * w, generator=torch.Generator().manual_seed(g["control_seed"])).to("cuda", torch.bfloat16)
+    ts = torch.tensor([g["timestep"]], device="cuda", dtype=torch.bfloat16)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        out, none = m.joint_forward(inp["latents"], timestep=ts, context=inp["context_pos"], y=inp["y"], use_gradient_checkpointing=False,
+                                    control_camera_latents_input=control)
+    assert none is None and out.shape == g["out"].shape
+    e = rel_err(out.cpu(), g["out"])
+    assert e < 3e-2, e

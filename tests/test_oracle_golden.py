@@ -97,3 +97,19 @@ def test_bf16_emulation_stays_close_to_fp32():
     out, _, _ = O.joint_forward(sd, inp["latents"], torch.tensor([gj["timestep"]]), inp["context_pos"], inp["clip_feature"],
                                 inp["y"], inp["plucker_fea"], start_index=1, n_irg=1, nm=O.BF16)
     assert rel_err(out, gj["out"]) < 3e-2
+
+
+def test_wan22_joint_forward_reduced():
+    """Wan2.2-Fun-A14B-Control-Camera variant (no CLIP, control adapter): oracle vs the reference's model_wan22.joint_forward."""
+    import json
+    from _common import GOLD
+    from fwb200.synth import synth_inputs, synth_tensor
+    g = gold("joint_forward_wan22.pt")
+    schema = json.loads((GOLD / "schema_wan22_reduced.json").read_text())
+    sd = {k: synth_tensor(k, shape, 0, "cpu") for k, shape in schema.items()}
+    f, h, w = g["grid"]
+    inp = synth_inputs(f, h, w, device="cpu", seed=1024, text_len=g["text_len"], dtype=torch.float32)
+    control = torch.randn(1, 24, f, 16 * h, 16 * w, generator=torch.Generator().manual_seed(g["control_seed"]))
+    out, _, _ = O.joint_forward(sd, inp["latents"], torch.tensor([g["timestep"]]), inp["context_pos"], None, inp["y"], None,
+                                start_index=1, n_irg=1, control=control)
+    assert rel_err(out, g["out"]) < TOL, rel_err(out, g["out"])
