@@ -39,6 +39,11 @@ struct AttnParams {
   int Lq, Lk, d_real;
   float scale_log2;
   int accumulate;  // out = bf16(out + bf16(result))  (sum of two attentions sharing q: wan_video_dit.py:197-200)
+  // split-KV mode (sequence parallel pipelining): write the subset-normalised result in fp32 and the row log-sum-exp
+  // (base 2, scale folded in) so that fwb_attn_merge can combine the partial attentions over disjoint key subsets.
+  float* part_out;   // [B, Lq, H, d_real] fp32 contiguous, or nullptr
+  float* part_lse;   // [B, H, Lq] fp32, or nullptr
+  int H;
 };
 
 template <int D>
@@ -284,12 +289,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int row = (qblock * 2 + i) * BQ + quad * 32 + lane;
     const float inv_l = 1.f / l_sum;
     __nv_bfloat16* orow = p.out + (long long)batch * p.o_sb + (long long)row * p.o_sl + (long long)head * p.o_sh;
+    if (p.part_lse && row < p.Lq) p.part_lse[((long long)batch * p.H + head) * p.Lq + row] = m_used + log2f(l_sum);
 #pragma unroll
     for (int c0 = 0; c0 < D; c0 += 32) {
       uint32_t o[32];
       tmem_ld32(o_tmem + c0, o);
       tmem_ld_wait();
-      if (row < p.Lq && c0 < p.d_real) {
+      if (p.part_out) {
+        if (row < p.Lq && c0 < p.d_real) {
+          float* prow = p.part_out + (((long long)batch * p.Lq + row) * p.H + head) * p.d_real + c0;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4)
+            *reinterpret_cast<float4*>(prow + c) = make_float4(__uint_as_float(o[c]) * inv_l, __uint_as_float(o[c + 1]) * inv_l,
+                                                               __uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+        }
+      } else if (row < p.Lq && c0 < p.d_real) {
 #pragma unroll
         for (int c = 0; c < 32; c += 8) {
           float y[8];
@@ -351,6 +365,39 @@ int launch_attn_emu(int emu, const CUtensorMap& tq, const CUtensorMap& tk, const
   }
 }
 
+// out[b,l,h,:] = sum_s w_s part[s][b,l,h,:] / sum_s w_s,  w_s = 2^(lse[s][b,h,l] - max_s lse)   (fp32 in, bf16 out)
+__global__ void attn_merge_kernel(const float* __restrict__ part, const float* __restrict__ lse, __nv_bfloat16* __restrict__ out,
+                                  long long o_sb, long long o_sl, long long o_sh, int S, int B, int H, int L, int D) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 8 output elements
+  const int pieces = D / 8;
+  const long long total = (long long)B * L * H * pieces;
+  if (gid >= total) return;
+  const int pc = (int)(gid % pieces);
+  const int h = (int)((gid / pieces) % H);
+  const long long l = (gid / ((long long)pieces * H)) % L;
+  const int b = (int)(gid / ((long long)pieces * H * L));
+  const long long lse_idx = ((long long)b * H + h) * L + l, lse_stride = (long long)B * H * L;
+  const long long part_idx = ((((long long)b * L + l) * H + h) * D) + pc * 8, part_stride = (long long)B * L * H * D;
+  float m = -INFINITY;
+  for (int s = 0; s < S; ++s) m = fmaxf(m, lse[lse_idx + s * lse_stride]);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, wsum = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const float w = fast_exp2(lse[lse_idx + s * lse_stride] - m);
+    wsum += w;
+    const float4 a = *reinterpret_cast<const float4*>(part + part_idx + s * part_stride);
+    const float4 c = *reinterpret_cast<const float4*>(part + part_idx + s * part_stride + 4);
+    acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
+    acc[4] += w * c.x; acc[5] += w * c.y; acc[6] += w * c.z; acc[7] += w * c.w;
+  }
+  const float inv = 1.f / wsum;
+  uint4 o;
+  o.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
+  o.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
+  o.z = pack_bf16x2(acc[4] * inv, acc[5] * inv);
+  o.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
+  *reinterpret_cast<uint4*>(out + b * o_sb + l * o_sl + h * o_sh + pc * 8) = o;
+}
+
 int g_attn_emu = -1;  // -1: default (0: measured fastest on B200, the softmax is issue-bound not MUFU-bound); 0..3: number of
                       // softmax elements out of every 4 that use exp2_poly
 
@@ -361,9 +408,40 @@ extern "C" int fwb_attn_set_tuning(int exp2_poly_quarters) {
   return FWB_OK;
 }
 
+static int attn_impl(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v, const fwb_tensor4_t* out, int B, int H,
+                     int Lq, int Lk, int D, float scale, int accumulate, float* part_out, float* part_lse, cudaStream_t stream);
+
 extern "C" int fwb_attn_fwd(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v,
                             const fwb_tensor4_t* out, int B, int H, int Lq, int Lk, int D, float scale,
                             int accumulate, cudaStream_t stream) {
+  FWB_CHECK(out && out->ptr, "attn: null output");
+  return attn_impl(q, k, v, out, B, H, Lq, Lk, D, scale, accumulate, nullptr, nullptr, stream);
+}
+
+extern "C" int fwb_attn_fwd_partial(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v, float* part_out,
+                                    float* part_lse, int B, int H, int Lq, int Lk, int D, float scale, cudaStream_t stream) {
+  FWB_CHECK(part_out && part_lse, "attn_partial: null output");
+  FWB_CHECK((reinterpret_cast<uintptr_t>(part_out) & 15) == 0, "attn_partial: part_out must be 16-byte aligned");
+  fwb_tensor4_t dummy = *q;   // only validated, never written in partial mode
+  return attn_impl(q, k, v, &dummy, B, H, Lq, Lk, D, scale, 0, part_out, part_lse, stream);
+}
+
+extern "C" int fwb_attn_merge(const float* part, const float* lse, const fwb_tensor4_t* out, int S, int B, int H, int L, int D,
+                              cudaStream_t stream) {
+  FWB_CHECK(part && lse && out && out->ptr, "attn_merge: null pointer");
+  FWB_CHECK(S >= 1 && B > 0 && H > 0 && L > 0 && D % 8 == 0, "attn_merge: bad shape");
+  FWB_CHECK(out->sb % 8 == 0 && out->sl % 8 == 0 && out->sh % 8 == 0 && (reinterpret_cast<uintptr_t>(out->ptr) & 15) == 0,
+            "attn_merge: output strides must be multiples of 8 elements and the pointer 16-byte aligned");
+  const long long total = (long long)B * L * H * (D / 8);
+  const long long blocks = (total + 255) / 256;
+  attn_merge_kernel<<<(unsigned)blocks, 256, 0, stream>>>(part, lse, reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(out->ptr)),
+                                                          out->sb, out->sl, out->sh, S, B, H, L, D);
+  FWB_CUDA(cudaGetLastError());
+  return FWB_OK;
+}
+
+static int attn_impl(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v, const fwb_tensor4_t* out, int B, int H,
+                     int Lq, int Lk, int D, float scale, int accumulate, float* part_out, float* part_lse, cudaStream_t stream) {
   FWB_CHECK(q && k && v && out && q->ptr && k->ptr && v->ptr && out->ptr, "attn: null pointer");
   FWB_CHECK(D == 64 || D == 96 || D == 128, "attn: head_dim %d unsupported (64, 96, 128)", D);
   FWB_CHECK(B > 0 && H > 0 && Lq > 0 && Lk > 0, "attn: empty problem B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk);
@@ -384,6 +462,9 @@ extern "C" int fwb_attn_fwd(const fwb_tensor4_t* q, const fwb_tensor4_t* k, cons
   p.Lq = Lq; p.Lk = Lk; p.d_real = D;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.accumulate = accumulate;
+  p.part_out = part_out;
+  p.part_lse = part_lse;
+  p.H = H;
   if (D == 64) return launch_attn_emu<64>(g_attn_emu >= 0 ? g_attn_emu : 0, tq, tk, tv, p, B, H, stream);
   return launch_attn_emu<128>(g_attn_emu >= 0 ? g_attn_emu : 0, tq, tk, tv, p, B, H, stream);
 }

@@ -52,6 +52,8 @@ def _load():
     lib.fwb_gemm_set_mode.argtypes = [i32]
     lib.fwb_attn_set_tuning.argtypes = [i32]
     lib.fwb_attn_fwd.argtypes = [C.POINTER(Tensor4)] * 4 + [i32, i32, i32, i32, i32, f32, i32, vp]
+    lib.fwb_attn_fwd_partial.argtypes = [C.POINTER(Tensor4)] * 3 + [vp, vp, i32, i32, i32, i32, i32, f32, vp]
+    lib.fwb_attn_merge.argtypes = [vp, vp, C.POINTER(Tensor4), i32, i32, i32, i32, i32, vp]
     lib.fwb_bringup_mma.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
     lib.fwb_ln_modulate.argtypes = [vp, i32, i64, i32, i32, f32, vp, vp, vp, vp, vp, i64, vp]
     lib.fwb_rmsnorm_rope.argtypes = [vp, i64, i32, i32, vp, f32, vp, i32, vp]

@@ -185,8 +185,8 @@ def dit_self_attn(sa, h, cos_sin, x_resid, gate):
     L = h.shape[0]
     H, D = sa.num_heads, sa.head_dim
     C = H * D
-    q = lin(h, sa.q)
     if SP is None:
+        q = lin(h, sa.q)
         k = lin(h, sa.k)
         v = lin(h, sa.v)
         ops.rmsnorm_rope_(q, w=f32(sa.norm_q, "w", sa.norm_q.weight), eps=sa.norm_q.eps, cos_sin=cos_sin, head_dim=D)
@@ -194,16 +194,35 @@ def dit_self_attn(sa, h, cos_sin, x_resid, gate):
         o = ops.attention(q.view(1, L, H, D), k.view(1, L, H, D), v.view(1, L, H, D))
     else:
         # sequence parallel: h holds this rank's L/P tokens.  K and V are written side by side into one packed buffer so
-        # that a single all-gather moves both; queries stay local.
+        # that a single exchange moves both; queries stay local.
         kv = torch.empty((L, 2 * C), device=h.device, dtype=BF16)
         lin(h, sa.k, out=kv[:, :C])
         lin(h, sa.v, out=kv[:, C:])
-        ops.rmsnorm_rope_(q, w=f32(sa.norm_q, "w", sa.norm_q.weight), eps=sa.norm_q.eps, cos_sin=cos_sin, head_dim=D)
         ops.rmsnorm_rope_(kv[:, :C], w=f32(sa.norm_k, "w", sa.norm_k.weight), eps=sa.norm_k.eps, cos_sin=cos_sin, head_dim=D)
-        kv_all = SP.all_gather_rows(kv, SP.layout.video_rows)
-        Lk = kv_all.shape[0]
-        o = ops.attention(q.view(1, L, H, D), kv_all[:, :C].unflatten(1, (H, D)).unsqueeze(0),
-                          kv_all[:, C:].unflatten(1, (H, D)).unsqueeze(0))
+        rows = SP.layout.video_rows
+        S = SP.kv_chunks if (len(set(rows)) == 1 and L >= 256 * SP.kv_chunks) else 1
+
+        def heads(t):
+            return t.unflatten(1, (H, D)).unsqueeze(0)
+
+        if S == 1:
+            kv_all = SP.all_gather_rows(kv, rows)
+            q = ops.rmsnorm_rope_(lin(h, sa.q), w=f32(sa.norm_q, "w", sa.norm_q.weight), eps=sa.norm_q.eps, cos_sin=cos_sin, head_dim=D)
+            o = ops.attention(q.view(1, L, H, D), heads(kv_all[:, :C]), heads(kv_all[:, C:]))
+        else:
+            # pipelined exchange: gather the K|V rows in S slices on a side stream; the q projection and then the attention
+            # over slice c (split-KV partials) run while slice c+1 is still in flight; one merge at the end.  Keys form a set,
+            # so the slice order is irrelevant to the result.
+            pending = SP.gather_chunks_async(kv, S)
+            q = ops.rmsnorm_rope_(lin(h, sa.q), w=f32(sa.norm_q, "w", sa.norm_q.weight), eps=sa.norm_q.eps, cos_sin=cos_sin, head_dim=D)
+            q4 = q.view(1, L, H, D)
+            part = torch.empty((S, 1, L, H, D), device=h.device, dtype=torch.float32)
+            lse = torch.empty((S, 1, H, L), device=h.device, dtype=torch.float32)
+            main = torch.cuda.current_stream()
+            for c, (buf, ev) in enumerate(pending):
+                main.wait_event(ev)
+                ops.attention_partial(q4, heads(buf[:, :C]), heads(buf[:, C:]), part[c], lse[c])
+            o = ops.attention_merge(part, lse)
     return lin(o.view(L, C), sa.o, scale1=gate, resid=x_resid, round_flags=ROUND_AFTER_BIAS | ROUND_AFTER_AFFINE)
 
 

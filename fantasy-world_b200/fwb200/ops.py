@@ -15,7 +15,7 @@ DT_BF16, DT_F32 = 0, 1
 __all__ = [
     "ACT_NONE", "ACT_GELU_TANH", "ACT_GELU_ERF", "ACT_RELU", "ACT_SILU",
     "ROUND_AFTER_BIAS", "ROUND_AFTER_ACT", "ROUND_AFTER_AFFINE", "ROUND_AFTER_SCALE2",
-    "device_ok", "require_device", "linear", "attention", "bringup_mma",
+    "device_ok", "require_device", "linear", "attention", "attention_partial", "attention_merge", "bringup_mma",
     "ln_modulate", "rmsnorm_rope_", "ln64_rope2d_", "cfg_euler_step_", "launch_count", "reset_launch_count",
     "prof_enable", "prof_disable",
 ]
@@ -191,6 +191,35 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
         check(lib.fwb_attn_fwd(C.byref(tq), C.byref(tk), C.byref(tv), C.byref(to), B, H, Lq, Lk, D, float(scale), int(accumulate),
                                _stream()), "fwb_attn_fwd")
     _nan_check(f"attn:B{B}:H{H}:Lq{Lq}:Lk{Lk}:D{D}:acc{int(accumulate)}", out)
+    return out
+
+
+def attention_partial(q, k, v, part_out: torch.Tensor, part_lse: torch.Tensor, *, scale: float | None = None):
+    """Attention of q over ONE subset of the keys: fp32 subset-normalised result into part_out [B, Lq, H, D] and the base-2 row
+    log-sum-exp into part_lse [B, H, Lq] (see attention_merge)."""
+    B, Lq, H, D = q.shape
+    Lk = k.shape[1]
+    if scale is None:
+        scale = 1.0 / math.sqrt(D)
+    assert part_out.shape == (B, Lq, H, D) and part_out.dtype == torch.float32 and part_out.is_contiguous()
+    assert part_lse.shape == (B, H, Lq) and part_lse.dtype == torch.float32 and part_lse.is_contiguous()
+    tq, tk, tv = _t4(q), _t4(k), _t4(v)
+    _count()
+    with _Rec(f"attn:B{B}:H{H}:Lq{Lq}:Lk{Lk}:D{D}"):
+        check(lib.fwb_attn_fwd_partial(C.byref(tq), C.byref(tk), C.byref(tv), part_out.data_ptr(), part_lse.data_ptr(), B, H, Lq, Lk,
+                                       D, float(scale), _stream()), "fwb_attn_fwd_partial")
+
+
+def attention_merge(part: torch.Tensor, lse: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Combine S partial attentions (part [S, B, L, H, D] fp32, lse [S, B, H, L]) into the bf16 result [B, L, H, D]."""
+    S, B, L, H, D = part.shape
+    assert lse.shape == (S, B, H, L) and part.is_contiguous() and lse.is_contiguous()
+    if out is None:
+        out = torch.empty((B, L, H, D), device=part.device, dtype=torch.bfloat16)
+    to = _t4(out)
+    _count()
+    with _Rec(f"attnmerge:S{S}:L{L}:H{H}:D{D}"):
+        check(lib.fwb_attn_merge(part.data_ptr(), lse.data_ptr(), C.byref(to), S, B, H, L, D, _stream()), "fwb_attn_merge")
     return out
 
 

@@ -85,6 +85,38 @@ class SPContext:
         self.layout: Optional[SPLayout] = None
         self.n_gathers = 0
         self.gather_bytes = 0
+        # pipelined K|V exchange: the local K|V rows are gathered in `kv_chunks` row slices on a side stream, and the attention
+        # over slice c (split-KV partial + merge) overlaps the gather of slice c+1.  1 = single blocking gather.
+        self.kv_chunks = 4 if self.world >= 4 else (2 if self.world > 1 else 1)
+        self._comm_stream = None
+
+    @property
+    def comm_stream(self):
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(priority=-1)
+        return self._comm_stream
+
+    def gather_chunks_async(self, x: torch.Tensor, n_chunks: int):
+        """Start all-gathers of `n_chunks` contiguous row slices of x (equal [rows, C] block on every rank) on the side
+        stream.  Returns [(buffer [world * rows_c, C], event)], in slice order; wait on the event before reading the buffer."""
+        rows = x.shape[0]
+        sizes = split_even(rows, n_chunks)
+        offs = offsets(sizes)
+        main = torch.cuda.current_stream()
+        bufs = [torch.empty((self.world * n, *x.shape[1:]), device=x.device, dtype=x.dtype) for n in sizes]
+        ready = torch.cuda.Event()
+        ready.record(main)
+        out = []
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ready)
+            for c, n in enumerate(sizes):
+                dist.all_gather_into_tensor(bufs[c], x[offs[c]: offs[c] + n], group=self.group)
+                ev = torch.cuda.Event()
+                ev.record(self.comm_stream)
+                out.append((bufs[c], ev))
+                self.n_gathers += 1
+                self.gather_bytes += bufs[c].numel() * bufs[c].element_size()
+        return out
 
     def set_grid(self, f, h, w):
         if self.layout is None or (self.layout.f, self.layout.h, self.layout.w) != (f, h, w):

@@ -86,6 +86,16 @@ typedef struct {
 int fwb_attn_fwd(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v, const fwb_tensor4_t* out, int B,
                  int H, int Lq, int Lk, int D, float scale, int accumulate, fwb_stream_t stream);
 
+/* Split-KV attention (sequence-parallel pipelining: attention over the key chunk that has already arrived overlaps the
+ * all-gather of the next chunk).  fwb_attn_fwd_partial writes, for one disjoint subset of the keys, the subset-normalised
+ * result in fp32 (part_out [B, Lq, H, D]) and the row log-sum-exp in base 2 with the scale folded in (part_lse [B, H, Lq]);
+ * fwb_attn_merge combines S such partials (part [S, B, Lq, H, D], lse [S, B, H, Lq]) into the bf16 output:
+ * out = sum_s 2^(lse_s - max) part_s / sum_s 2^(lse_s - max).  Mathematically identical to one fwb_attn_fwd over all keys. */
+int fwb_attn_fwd_partial(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v, float* part_out, float* part_lse,
+                         int B, int H, int Lq, int Lk, int D, float scale, fwb_stream_t stream);
+int fwb_attn_merge(const float* part, const float* lse, const fwb_tensor4_t* out, int S, int B, int H, int L, int D,
+                   fwb_stream_t stream);
+
 /* Tuning hook: how many of every 4 softmax elements use the FMA-pipe exp2 polynomial instead of MUFU.EX2
  * (-1 = built-in default per head_dim, 0 = MUFU only ... 3).  Changes results only below bf16 resolution of P. */
 int fwb_attn_set_tuning(int exp2_poly_quarters);

@@ -146,6 +146,31 @@ def test_attention_strided_views_and_accumulate(fwb):
     torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=1.2e-2)
 
 
+def test_attention_split_kv_partials_and_merge(fwb):
+    """Split-KV mode used by the sequence-parallel pipeline: partial attentions over disjoint key subsets + merge == one
+    attention over all keys (up to fp32 re-association before the single bf16 rounding)."""
+    torch.manual_seed(11)
+    B, H, Lq, D = 1, 5, 700, 128
+    sizes = [256, 900, 333]
+    q = _bf(torch.randn(B, Lq, H, D, device="cuda"))
+    k = _bf(torch.randn(B, sum(sizes), H, D, device="cuda") * 1.5)
+    v = _bf(torch.randn(B, sum(sizes), H, D, device="cuda"))
+    part = torch.empty(len(sizes), B, Lq, H, D, device="cuda")
+    lse = torch.empty(len(sizes), B, H, Lq, device="cuda")
+    o = 0
+    for i, n in enumerate(sizes):
+        fwb.attention_partial(q, k[:, o:o + n], v[:, o:o + n], part[i], lse[i])
+        o += n
+    merged = fwb.attention_merge(part, lse)
+    full = fwb.attention(q, k, v)
+    torch.testing.assert_close(merged.float(), _attn_ref(q, k, v), rtol=2e-2, atol=6e-3)
+    assert (merged.float() - full.float()).abs().max() <= 2 ** -7 * full.float().abs().max()   # at most a bf16 ulp apart
+    # lse is the base-2 log-sum-exp of the scaled scores
+    s = (q.float().permute(0, 2, 1, 3) @ k[:, :sizes[0]].float().permute(0, 2, 3, 1)) / math.sqrt(D)
+    ref_lse = torch.logsumexp(s, dim=-1) / math.log(2)
+    torch.testing.assert_close(lse[0], ref_lse, rtol=1e-4, atol=2e-3)
+
+
 def test_attention_softmax_rows_sum_to_one_full_size(fwb):
     """Size-independent property at the BASELINE C2 size (L = 32760 tokens, 128-dim heads): with V = 1 the output is 1."""
     torch.manual_seed(2)
