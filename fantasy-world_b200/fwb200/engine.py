@@ -355,14 +355,31 @@ def bicross(blk, x1, x2, cs_dit, cs_agg):
         o1 = ops.attention(q, k, v2)   # video <- geometry
         o2 = ops.attention(k, q, v1)   # geometry <- video
     else:
-        qv1_all = SP.all_gather_rows(qv1, SP.layout.video_rows)      # [L, 2E]
-        kv2_all = SP.all_gather_rows(kv2, SP.layout.geo_rows())      # [N, 2E]
-
         def heads(t):
             return t.unflatten(1, (H, D)).unsqueeze(0)
 
-        o1 = ops.attention(q, heads(kv2_all[:, :E]), heads(kv2_all[:, E:]))   # local video queries x all geometry keys
-        o2 = ops.attention(k, heads(qv1_all[:, :E]), heads(qv1_all[:, E:]))   # local geometry queries x all video keys
+        # both exchanges start on the side stream; the [q|v1] rows (needed by the geometry queries) travel in slices while the
+        # video queries already attend over the gathered [k|v2]
+        finish_kv2 = SP.all_gather_rows_async(kv2, SP.layout.geo_rows())                 # ragged frame-aligned shards
+        rows = SP.layout.video_rows
+        S = SP.kv_chunks if (len(set(rows)) == 1 and L1 >= 256 * SP.kv_chunks) else 1
+        if S == 1:
+            finish_qv1 = SP.all_gather_rows_async(qv1, rows)
+            kv2_all = finish_kv2()                                                        # [N, 2E]
+            o1 = ops.attention(q, heads(kv2_all[:, :E]), heads(kv2_all[:, E:]))           # local video queries x all geometry keys
+            qv1_all = finish_qv1()                                                        # [L, 2E]
+            o2 = ops.attention(k, heads(qv1_all[:, :E]), heads(qv1_all[:, E:]))           # local geometry queries x all video keys
+        else:
+            pending = SP.gather_chunks_async(qv1, S)
+            kv2_all = finish_kv2()
+            o1 = ops.attention(q, heads(kv2_all[:, :E]), heads(kv2_all[:, E:]))
+            part = torch.empty((S, 1, L2, H, D), device=x1.device, dtype=torch.float32)
+            lse = torch.empty((S, 1, H, L2), device=x1.device, dtype=torch.float32)
+            main = torch.cuda.current_stream()
+            for c, (buf, ev) in enumerate(pending):
+                main.wait_event(ev)
+                ops.attention_partial(k, heads(buf[:, :E]), heads(buf[:, E:]), part[c], lse[c])
+            o2 = ops.attention_merge(part, lse)
     rf = ROUND_AFTER_BIAS | ROUND_AFTER_AFFINE
     x1 = lin(o1.view(L1, E), ca.out_m1_proj, scale1=f32(blk, "g1", blk.gamma_m1), resid=x1, round_flags=rf)
     x2 = lin(o2.view(L2, E), ca.out_m2_proj, scale1=f32(blk, "g2", blk.gamma_m2), resid=x2, out_dtype=x2.dtype,

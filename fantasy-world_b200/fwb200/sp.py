@@ -118,6 +118,37 @@ class SPContext:
                 self.gather_bytes += bufs[c].numel() * bufs[c].element_size()
         return out
 
+    def all_gather_rows_async(self, x: torch.Tensor, sizes: List[int]):
+        """all_gather_rows on the side stream.  Returns a function that waits for the exchange and yields [sum(sizes), C]."""
+        assert x.is_contiguous() and x.shape[0] == sizes[self.rank]
+        m = max(sizes)
+        C = x.shape[1:]
+        if x.shape[0] < m:
+            xp = torch.zeros((m, *C), device=x.device, dtype=x.dtype)
+            xp[: x.shape[0]] = x
+        else:
+            xp = x
+        buf = torch.empty((self.world * m, *C), device=x.device, dtype=x.dtype)
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        ev = torch.cuda.Event()
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ready)
+            dist.all_gather_into_tensor(buf, xp, group=self.group)
+            ev.record(self.comm_stream)
+        self.n_gathers += 1
+        self.gather_bytes += buf.numel() * buf.element_size()
+
+        def finish():
+            torch.cuda.current_stream().wait_event(ev)
+            if len(set(sizes)) == 1:
+                return buf
+            b3 = buf.view(self.world, m, *C)
+            return torch.cat([b3[r, : sizes[r]] for r in range(self.world)], dim=0)
+
+        return finish
+
     def set_grid(self, f, h, w):
         if self.layout is None or (self.layout.f, self.layout.h, self.layout.w) != (f, h, w):
             self.layout = SPLayout(self.world, f, h, w)
