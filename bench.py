@@ -201,7 +201,10 @@ def run_ours(args):
 
     # ---- timed region: device-resident inputs --------------------------------------------------------------------------
     L = f * h * w
-    dom_tag = f"attn:B1:H40:Lq{L // world}:Lk{L}:D128"
+    # dominant kernel: DiT self-attention.  Under sequence parallelism with the pipelined exchange every attention runs as
+    # `kv_chunks` split-KV partials over L / kv_chunks keys each.
+    chunks = model.sp.kv_chunks if (world > 1 and (L // world) >= 256 * model.sp.kv_chunks) else 1
+    dom_tag = f"attn:B1:H40:Lq{L // world}:Lk{L // chunks}:D128"
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -260,7 +263,7 @@ def run_ours(args):
     if dom_tag in prof:
         cnt, tot = prof[dom_tag]
         per = tot / cnt
-        fl = 4.0 * 40 * (L // world) * L * 128
+        fl = 4.0 * 40 * (L // world) * (L // chunks) * 128
         ach = fl / (per * 1e-3) / 1e12
         traffic = None
         tp = ROOT / "profiles" / "attn_d128_dram_bytes.json"
@@ -299,7 +302,7 @@ def run_ours(args):
     if args.breakdown:
         agg = sorted(((t, c, ms_) for t, (c, ms_) in prof.items()), key=lambda r: -r[2])
         line["breakdown_ms_per_step"] = [{"tag": t, "launches_per_step": c / args.steps, "ms_per_step": m / args.steps} for t, c, m in agg[:40]]
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def main():
