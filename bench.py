@@ -92,13 +92,37 @@ def peaks():
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port of the reference's algorithm on the host cores (bounded sample)
 # ----------------------------------------------------------------------------------------------------------------------
+def usable_cores():
+    """Host threads this process can really use: the affinity mask, capped by the cgroup CPU quota when there is one
+    (os.cpu_count() reports the machine, and oversubscribing a quota makes the CPU arm look worse than it is)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = Path(path).read_text().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                per = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+                if q > 0:
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    return n
+
+
 def cpu_sample(f=1, h=30, w=52, text_len=512, reps=1):
     """One PCB DiT block + one VGGT frame block + one IRG block at f,h,w (full 14B widths), fp32, all host threads.
     Returns (seconds, algorithmic FLOPs, description)."""
     import torch
     from fwb200.synth import synth_tensor
     from oracle import fw_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(usable_cores())
     schema = json.loads((ROOT / "tests" / "golden" / "schema_reduced.json").read_text())
     keys = [k for k in schema if k.startswith(("pipe.dit.blocks.0.", "vggt.aggregator.frame_blocks.0.", "IRGBlock.0.",
                                                 "vggt.aggregator.camera_token", "vggt.aggregator.register_token"))]
@@ -131,7 +155,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     times, flops, desc = [], 0.0, ""
     for i in range(args.warmup + args.steps):
         dt, flops, desc = cpu_sample(reps=1)
@@ -141,7 +165,7 @@ def run_reference(args):
     rate = flops / dt                                   # FLOP/s of the reference algorithm on this host
     steps_per_s = rate / STEP_FLOP_C2
     line = {"metric": "denoise_steps_per_sec", "value": steps_per_s, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 / steps_per_s, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 / steps_per_s, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": "Wan2.1-I2V-14B-480P shape, latents 1x16x21x60x104 (81 frames), 16 PCB + 24 IRG, CFG 2 forwards/step",
                        "note": "each timed step is a bounded sample; steps/s = measured FLOP/s / 4.267 PFLOP per step"},
@@ -149,7 +173,7 @@ def run_reference(args):
                              "sample_seconds": dt, "achieved_tflops": rate / 1e12},
             "e2e": {"value": steps_per_s, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -282,7 +306,7 @@ def run_ours(args):
     if not args.no_cpu_baseline:
         dt, cfl, desc = cpu_sample()
         rate = cfl / dt
-        cpu = {"value": rate / (2 * fwd_fl), "unit": "steps/s", "cores": os.cpu_count(), "kind": "port", "sample": desc,
+        cpu = {"value": rate / (2 * fwd_fl), "unit": "steps/s", "cores": usable_cores(), "kind": "port", "sample": desc,
                "sample_seconds": dt, "achieved_tflops": rate / 1e12}
     full = (f, h, w, n_pcb, n_irg) == (21, 30, 52, 16, 24)
     line = {"metric": "denoise_steps_per_sec", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
@@ -302,7 +326,29 @@ def run_ours(args):
     if args.breakdown:
         agg = sorted(((t, c, ms_) for t, (c, ms_) in prof.items()), key=lambda r: -r[2])
         line["breakdown_ms_per_step"] = [{"tag": t, "launches_per_step": c / args.steps, "ms_per_step": m / args.steps} for t, c, m in agg[:40]]
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def protect_stdout():
+    """Libraries (NCCL's version banner, torch warnings) may write to fd 1; the driver expects ONE JSON line there.  Keep a
+    private copy of stdout for the result and point fd 1 at stderr for everything else."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -319,6 +365,7 @@ def main():
     ap.add_argument("--breakdown", action="store_true", help="time every fwb200 launch with CUDA events and add a per-kernel table")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    protect_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

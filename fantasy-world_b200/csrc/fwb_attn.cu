@@ -44,6 +44,14 @@ struct AttnParams {
   float* part_out;   // [B, Lq, H, d_real] fp32 contiguous, or nullptr
   float* part_lse;   // [B, H, Lq] fp32, or nullptr
   int H;
+  // tile schedule (1-D grid).  A tile = 256 query rows x one (batch, head); tiles [0, n_full) are processed by one CTA each
+  // over all keys; each of the remaining `tail` tiles (the last, partly filled wave) is split over S CTAs along the keys
+  // (stream-K for the tail) which write (normalised fp32 O, lse) to the workspace; attn_tail_merge_kernel combines them.
+  int nq;            // query tiles per (batch, head)
+  int n_full;        // tiles processed unsplit
+  int S;             // key splits per tail tile (>= 2 when there is a split tail, else 1)
+  float* ws_out;     // [tail, S, 256, d_real]
+  float* ws_lse;     // [tail, S, 256]
 };
 
 template <int D>
@@ -87,8 +95,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const uint32_t warp = warp_id_uniform();
   const uint32_t lane = lane_id();
-  const int qblock = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
-  const int n_kv = (p.Lk + BKV - 1) / BKV;
+  // tile schedule (see AttnParams): decoded from blockIdx wherever it is needed instead of being kept live across the KV loop
+  auto decode = [&](int& tile, int& split, int& nsplit) {
+    tile = blockIdx.x; split = 0; nsplit = 1;
+    if (tile >= p.n_full) {
+      const int r = tile - p.n_full;
+      tile = p.n_full + r / p.S;
+      split = r % p.S;
+      nsplit = p.S;
+    }
+  };
+  int qblock, head, batch, kv0, n_kv, j_ragged;
+  {
+    int tile, split, nsplit;
+    decode(tile, split, nsplit);
+    qblock = tile % p.nq; head = (tile / p.nq) % p.H; batch = tile / (p.nq * p.H);
+    const int n_kv_all = (p.Lk + BKV - 1) / BKV;
+    kv0 = (int)((long long)split * n_kv_all / nsplit);       // this CTA's KV tiles: [kv0, kv0 + n_kv)
+    n_kv = (int)((long long)(split + 1) * n_kv_all / nsplit) - kv0;
+    j_ragged = n_kv_all - 1 - kv0;                           // local index of the (possibly) partly filled last KV tile
+  }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -131,11 +157,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&k_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&k_full[s], Cfg::kTileBytes);
         for (int b = 0; b < Cfg::kBoxes; ++b)
-          tma_load_4d(sK + s * Cfg::kTileBytes + b * 16384, &tmK, &k_full[s], b * 64, head, j * BKV, batch);
+          tma_load_4d(sK + s * Cfg::kTileBytes + b * 16384, &tmK, &k_full[s], b * 64, head, (kv0 + j) * BKV, batch);
         mbar_wait(&v_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[s], Cfg::kTileBytes);
         for (int b = 0; b < Cfg::kBoxes; ++b)
-          tma_load_4d(sV + s * Cfg::kTileBytes + b * 16384, &tmV, &v_full[s], b * 64, head, j * BKV, batch);
+          tma_load_4d(sV + s * Cfg::kTileBytes + b * 16384, &tmV, &v_full[s], b * 64, head, (kv0 + j) * BKV, batch);
       }
     }
   } else if (warp == 8) {
@@ -222,8 +248,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld32(s_tmem + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
       tmem_ld_wait();
 
-      if (j == n_kv - 1) {
-        const int valid = p.Lk - j * BKV;
+      if (j == j_ragged) {
+        const int valid = p.Lk - (kv0 + j) * BKV;
         if (valid < BKV) {
 #pragma unroll
           for (int c = 0; c < 128; ++c)
@@ -289,13 +315,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int row = (qblock * 2 + i) * BQ + quad * 32 + lane;
     const float inv_l = 1.f / l_sum;
     __nv_bfloat16* orow = p.out + (long long)batch * p.o_sb + (long long)row * p.o_sl + (long long)head * p.o_sh;
-    if (p.part_lse && row < p.Lq) p.part_lse[((long long)batch * p.H + head) * p.Lq + row] = m_used + log2f(l_sum);
+    const int row_in_tile = i * BQ + quad * 32 + lane;
+    float* ws_row = nullptr;
+    int tile, split, nsplit;
+    decode(tile, split, nsplit);
+    if (nsplit > 1) {
+      const long long slot = (long long)(tile - p.n_full) * p.S + split;
+      ws_row = p.ws_out + (slot * (2 * BQ) + row_in_tile) * p.d_real;
+      p.ws_lse[slot * (2 * BQ) + row_in_tile] = m_used + log2f(l_sum);
+    } else if (p.part_lse && row < p.Lq) {
+      p.part_lse[((long long)batch * p.H + head) * p.Lq + row] = m_used + log2f(l_sum);
+    }
 #pragma unroll
     for (int c0 = 0; c0 < D; c0 += 32) {
       uint32_t o[32];
       tmem_ld32(o_tmem + c0, o);
       tmem_ld_wait();
-      if (p.part_out) {
+      if (ws_row) {
+        if (c0 < p.d_real) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4)
+            *reinterpret_cast<float4*>(ws_row + c0 + c) =
+                make_float4(__uint_as_float(o[c]) * inv_l, __uint_as_float(o[c + 1]) * inv_l, __uint_as_float(o[c + 2]) * inv_l,
+                            __uint_as_float(o[c + 3]) * inv_l);
+        }
+      } else if (p.part_out) {
         if (row < p.Lq && c0 < p.d_real) {
           float* prow = p.part_out + (((long long)batch * p.Lq + row) * p.H + head) * p.d_real + c0;
 #pragma unroll
@@ -341,6 +385,48 @@ int make_qkv_map(CUtensorMap* m, const fwb_tensor4_t* t, int B, int H, int L, in
   return make_tmap_bf16(m, t->ptr, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+// Combine the S key-split partials of every tail tile and finish the row exactly as the unsplit epilogue would:
+// bf16 out, or (split-KV mode) the fp32 subset-normalised result + lse.  One thread per 8 output elements.
+__global__ void attn_tail_merge_kernel(const AttnParams p, int tail) {
+  const int pieces = p.d_real / 8;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)tail * (2 * BQ) * pieces) return;
+  const int pc = (int)(gid % pieces);
+  const int r = (int)((gid / pieces) % (2 * BQ));
+  const int t = (int)(gid / ((long long)pieces * 2 * BQ));
+  const int tile = p.n_full + t;
+  const int qblock = tile % p.nq, head = (tile / p.nq) % p.H, batch = tile / (p.nq * p.H);
+  const int row = qblock * 2 * BQ + r;
+  if (row >= p.Lq) return;
+  const float* lse = p.ws_lse + ((long long)t * p.S) * (2 * BQ) + r;
+  const float* po = p.ws_out + (((long long)t * p.S) * (2 * BQ) + r) * p.d_real + pc * 8;
+  float m = -INFINITY;
+  for (int s = 0; s < p.S; ++s) m = fmaxf(m, lse[s * 2 * BQ]);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, wsum = 0.f;
+  for (int s = 0; s < p.S; ++s) {
+    const float w = fast_exp2(lse[s * 2 * BQ] - m);
+    wsum += w;
+    const float4 a = *reinterpret_cast<const float4*>(po + (long long)s * 2 * BQ * p.d_real);
+    const float4 c = *reinterpret_cast<const float4*>(po + (long long)s * 2 * BQ * p.d_real + 4);
+    acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
+    acc[4] += w * c.x; acc[5] += w * c.y; acc[6] += w * c.z; acc[7] += w * c.w;
+  }
+  const float inv = 1.f / wsum;
+  if (p.part_out) {
+    float* dst = p.part_out + (((long long)batch * p.Lq + row) * p.H + head) * p.d_real + pc * 8;
+    *reinterpret_cast<float4*>(dst) = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+    if (pc == 0) p.part_lse[((long long)batch * p.H + head) * p.Lq + row] = m + log2f(wsum);
+  } else {
+    uint4 o;
+    o.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
+    o.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
+    o.z = pack_bf16x2(acc[4] * inv, acc[5] * inv);
+    o.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
+    *reinterpret_cast<uint4*>(p.out + (long long)batch * p.o_sb + (long long)row * p.o_sl + (long long)head * p.o_sh + pc * 8) = o;
+  }
+}
+
 template <int D, int EMU>
 int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B, int H,
                 cudaStream_t stream) {
@@ -350,9 +436,17 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
     FWB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  dim3 grid((p.Lq + 2 * BQ - 1) / (2 * BQ), H, B);
-  attn_fwd_kernel<D, EMU><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  const long long n_tiles = (long long)p.nq * H * B;
+  const long long tail = n_tiles - p.n_full;
+  const long long grid = p.n_full + (p.S > 1 ? tail * p.S : tail);
+  FWB_CHECK(grid < (1ll << 31), "attn: grid too large");
+  attn_fwd_kernel<D, EMU><<<(unsigned)grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
   FWB_CUDA(cudaGetLastError());
+  if (p.S > 1) {
+    const long long total = tail * (2 * BQ) * (p.d_real / 8);
+    attn_tail_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, (int)tail);
+    FWB_CUDA(cudaGetLastError());
+  }
   return FWB_OK;
 }
 
@@ -398,32 +492,44 @@ __global__ void attn_merge_kernel(const float* __restrict__ part, const float* _
   *reinterpret_cast<uint4*>(out + b * o_sb + l * o_sl + h * o_sh + pc * 8) = o;
 }
 
+int g_attn_tail_split = 1;  // fwb_attn_set_tuning(100 / 101) turns the tail split off / on (A/B measurements)
 int g_attn_emu = -1;  // -1: default (0: measured fastest on B200, the softmax is issue-bound not MUFU-bound); 0..3: number of
                       // softmax elements out of every 4 that use exp2_poly
 
 }  // namespace
 
 extern "C" int fwb_attn_set_tuning(int exp2_poly_quarters) {
+  if (exp2_poly_quarters == 100 || exp2_poly_quarters == 101) {
+    g_attn_tail_split = exp2_poly_quarters - 100;
+    return FWB_OK;
+  }
   g_attn_emu = exp2_poly_quarters;
   return FWB_OK;
 }
 
 static int attn_impl(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v, const fwb_tensor4_t* out, int B, int H,
-                     int Lq, int Lk, int D, float scale, int accumulate, float* part_out, float* part_lse, cudaStream_t stream);
+                     int Lq, int Lk, int D, float scale, int accumulate, float* part_out, float* part_lse, void* ws, size_t ws_bytes,
+                     cudaStream_t stream);
+
+extern "C" size_t fwb_attn_workspace_bytes(void) {
+  // at most one wave of split CTAs: (#SMs) x 256 rows x (128 + 1) floats
+  return (size_t)(num_sms() > 0 ? num_sms() : 148) * 2 * BQ * (128 + 1) * sizeof(float);
+}
 
 extern "C" int fwb_attn_fwd(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v,
                             const fwb_tensor4_t* out, int B, int H, int Lq, int Lk, int D, float scale,
-                            int accumulate, cudaStream_t stream) {
+                            int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   FWB_CHECK(out && out->ptr, "attn: null output");
-  return attn_impl(q, k, v, out, B, H, Lq, Lk, D, scale, accumulate, nullptr, nullptr, stream);
+  return attn_impl(q, k, v, out, B, H, Lq, Lk, D, scale, accumulate, nullptr, nullptr, workspace, workspace_bytes, stream);
 }
 
 extern "C" int fwb_attn_fwd_partial(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v, float* part_out,
-                                    float* part_lse, int B, int H, int Lq, int Lk, int D, float scale, cudaStream_t stream) {
+                                    float* part_lse, int B, int H, int Lq, int Lk, int D, float scale, void* workspace,
+                                    size_t workspace_bytes, cudaStream_t stream) {
   FWB_CHECK(part_out && part_lse, "attn_partial: null output");
   FWB_CHECK((reinterpret_cast<uintptr_t>(part_out) & 15) == 0, "attn_partial: part_out must be 16-byte aligned");
   fwb_tensor4_t dummy = *q;   // only validated, never written in partial mode
-  return attn_impl(q, k, v, &dummy, B, H, Lq, Lk, D, scale, 0, part_out, part_lse, stream);
+  return attn_impl(q, k, v, &dummy, B, H, Lq, Lk, D, scale, 0, part_out, part_lse, workspace, workspace_bytes, stream);
 }
 
 extern "C" int fwb_attn_merge(const float* part, const float* lse, const fwb_tensor4_t* out, int S, int B, int H, int L, int D,
@@ -441,7 +547,8 @@ extern "C" int fwb_attn_merge(const float* part, const float* lse, const fwb_ten
 }
 
 static int attn_impl(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v, const fwb_tensor4_t* out, int B, int H,
-                     int Lq, int Lk, int D, float scale, int accumulate, float* part_out, float* part_lse, cudaStream_t stream) {
+                     int Lq, int Lk, int D, float scale, int accumulate, float* part_out, float* part_lse, void* ws, size_t ws_bytes,
+                     cudaStream_t stream) {
   FWB_CHECK(q && k && v && out && q->ptr && k->ptr && v->ptr && out->ptr, "attn: null pointer");
   FWB_CHECK(D == 64 || D == 96 || D == 128, "attn: head_dim %d unsupported (64, 96, 128)", D);
   FWB_CHECK(B > 0 && H > 0 && Lq > 0 && Lk > 0, "attn: empty problem B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk);
@@ -465,6 +572,34 @@ static int attn_impl(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_t
   p.part_out = part_out;
   p.part_lse = part_lse;
   p.H = H;
+  // ---- tile schedule: split the last, partly filled wave of tiles along the keys (needs a workspace; never in accumulate mode,
+  // whose read-modify-write epilogue belongs to the unsplit CTA) ----
+  p.nq = (Lq + 2 * BQ - 1) / (2 * BQ);
+  const long long n_tiles = (long long)p.nq * H * B;
+  FWB_CHECK(n_tiles < (1ll << 30), "attn: too many tiles");
+  p.n_full = (int)n_tiles;
+  p.S = 1;
+  p.ws_out = nullptr;
+  p.ws_lse = nullptr;
+  const int W = num_sms();
+  if (ws && !accumulate && g_attn_tail_split && W > 0 && n_tiles % W != 0) {
+    const long long full = (n_tiles / W) * W, tail = n_tiles - full;
+    const int n_kv_all = (Lk + BKV - 1) / BKV;
+    long long S = W / tail;
+    if (S > 16) S = 16;
+    if (S > n_kv_all / 4) S = n_kv_all / 4;      // at least 4 KV tiles per split
+    if (S >= 2) {
+      const double plain = (double)(full / W + 1);
+      const double split = (double)(full / W) + 1.0 / (double)S + 0.04;   // + prologue/epilogue of the short CTAs and the merge
+      const size_t need = (size_t)tail * S * 2 * BQ * (D + 1) * sizeof(float);
+      if (split <= 0.95 * plain && need <= ws_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
+        p.n_full = (int)full;
+        p.S = (int)S;
+        p.ws_out = reinterpret_cast<float*>(ws);
+        p.ws_lse = p.ws_out + (size_t)tail * S * 2 * BQ * D;
+      }
+    }
+  }
   if (D == 64) return launch_attn_emu<64>(g_attn_emu >= 0 ? g_attn_emu : 0, tq, tk, tv, p, B, H, stream);
   return launch_attn_emu<128>(g_attn_emu >= 0 ? g_attn_emu : 0, tq, tk, tv, p, B, H, stream);
 }

@@ -51,8 +51,8 @@ def _load():
     lib.fwb_gemm_bf16.argtypes = [vp, i64, vp, i64, i32, i32, i32, C.POINTER(Epilogue), vp]
     lib.fwb_gemm_set_mode.argtypes = [i32]
     lib.fwb_attn_set_tuning.argtypes = [i32]
-    lib.fwb_attn_fwd.argtypes = [C.POINTER(Tensor4)] * 4 + [i32, i32, i32, i32, i32, f32, i32, vp]
-    lib.fwb_attn_fwd_partial.argtypes = [C.POINTER(Tensor4)] * 3 + [vp, vp, i32, i32, i32, i32, i32, f32, vp]
+    lib.fwb_attn_fwd.argtypes = [C.POINTER(Tensor4)] * 4 + [i32, i32, i32, i32, i32, f32, i32, vp, C.c_size_t, vp]
+    lib.fwb_attn_fwd_partial.argtypes = [C.POINTER(Tensor4)] * 3 + [vp, vp, i32, i32, i32, i32, i32, f32, vp, C.c_size_t, vp]
     lib.fwb_attn_merge.argtypes = [vp, vp, C.POINTER(Tensor4), i32, i32, i32, i32, i32, vp]
     lib.fwb_bringup_mma.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
     lib.fwb_ln_modulate.argtypes = [vp, i32, i64, i32, i32, f32, vp, vp, vp, vp, vp, i64, vp]
@@ -64,6 +64,8 @@ def _load():
         if name not in ("fwb_last_error",):
             fn.restype = C.c_int if name != "fwb_last_error" else C.c_char_p
     lib.fwb_last_error.restype = C.c_char_p
+    lib.fwb_attn_workspace_bytes.restype = C.c_size_t
+    lib.fwb_attn_workspace_bytes.argtypes = []
     return lib
 
 

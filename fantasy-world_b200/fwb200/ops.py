@@ -175,6 +175,19 @@ def _t4(t: torch.Tensor) -> Tensor4:
     return r
 
 
+_attn_ws: dict = {}
+
+
+def _attn_workspace(device):
+    """Scratch for the tail split of the attention tile schedule (fwb_attn_workspace_bytes, ~20 MB), one per (device, stream)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _attn_ws.get(key)
+    if ws is None:
+        ws = torch.empty(int(lib.fwb_attn_workspace_bytes()), device=device, dtype=torch.uint8)
+        _attn_ws[key] = ws
+    return ws
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float | None = None, out=None,
               accumulate: bool = False) -> torch.Tensor:
     """softmax(scale * q k^T) v, non-causal. q [B, Lq, H, D], k/v [B, Lk, H, D] (bf16 views, D contiguous)."""
@@ -188,8 +201,9 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
     tq, tk, tv, to = _t4(q), _t4(k), _t4(v), _t4(out)
     _count()
     with _Rec(f"attn:B{B}:H{H}:Lq{Lq}:Lk{Lk}:D{D}"):
+        ws = _attn_workspace(q.device)
         check(lib.fwb_attn_fwd(C.byref(tq), C.byref(tk), C.byref(tv), C.byref(to), B, H, Lq, Lk, D, float(scale), int(accumulate),
-                               _stream()), "fwb_attn_fwd")
+                               ws.data_ptr(), ws.numel(), _stream()), "fwb_attn_fwd")
     _nan_check(f"attn:B{B}:H{H}:Lq{Lq}:Lk{Lk}:D{D}:acc{int(accumulate)}", out)
     return out
 
@@ -206,8 +220,9 @@ def attention_partial(q, k, v, part_out: torch.Tensor, part_lse: torch.Tensor, *
     tq, tk, tv = _t4(q), _t4(k), _t4(v)
     _count()
     with _Rec(f"attn:B{B}:H{H}:Lq{Lq}:Lk{Lk}:D{D}"):
+        ws = _attn_workspace(q.device)
         check(lib.fwb_attn_fwd_partial(C.byref(tq), C.byref(tk), C.byref(tv), part_out.data_ptr(), part_lse.data_ptr(), B, H, Lq, Lk,
-                                       D, float(scale), _stream()), "fwb_attn_fwd_partial")
+                                       D, float(scale), ws.data_ptr(), ws.numel(), _stream()), "fwb_attn_fwd_partial")
 
 
 def attention_merge(part: torch.Tensor, lse: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:

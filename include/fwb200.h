@@ -15,13 +15,14 @@
 #ifndef FWB200_H_
 #define FWB200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define FWB_ABI_VERSION 1
+#define FWB_ABI_VERSION 2
 
 typedef struct CUstream_st* fwb_stream_t; /* == cudaStream_t */
 
@@ -83,8 +84,14 @@ typedef struct {
   int64_t sb, sl, sh;
 } fwb_tensor4_t;
 
+/* workspace (optional, may be NULL / 0): device scratch of fwb_attn_workspace_bytes() bytes, 16-byte aligned, private to the
+ * stream.  With it, when the tile count (ceil(Lq/256) * H * B) leaves the last wave of CTAs partly empty, the tiles of that
+ * wave are split along the keys over the idle SMs and merged (same result up to one rounding of the merge weights).  This is
+ * what keeps the sequence-parallel shards (Lq = L / ranks) from losing up to a full wave per attention. */
+size_t fwb_attn_workspace_bytes(void);
 int fwb_attn_fwd(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v, const fwb_tensor4_t* out, int B,
-                 int H, int Lq, int Lk, int D, float scale, int accumulate, fwb_stream_t stream);
+                 int H, int Lq, int Lk, int D, float scale, int accumulate, void* workspace, size_t workspace_bytes,
+                 fwb_stream_t stream);
 
 /* Split-KV attention (sequence-parallel pipelining: attention over the key chunk that has already arrived overlaps the
  * all-gather of the next chunk).  fwb_attn_fwd_partial writes, for one disjoint subset of the keys, the subset-normalised
@@ -92,12 +99,13 @@ int fwb_attn_fwd(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tenso
  * fwb_attn_merge combines S such partials (part [S, B, Lq, H, D], lse [S, B, H, Lq]) into the bf16 output:
  * out = sum_s 2^(lse_s - max) part_s / sum_s 2^(lse_s - max).  Mathematically identical to one fwb_attn_fwd over all keys. */
 int fwb_attn_fwd_partial(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v, float* part_out, float* part_lse,
-                         int B, int H, int Lq, int Lk, int D, float scale, fwb_stream_t stream);
+                         int B, int H, int Lq, int Lk, int D, float scale, void* workspace, size_t workspace_bytes,
+                         fwb_stream_t stream);
 int fwb_attn_merge(const float* part, const float* lse, const fwb_tensor4_t* out, int S, int B, int H, int L, int D,
                    fwb_stream_t stream);
 
 /* Tuning hook: how many of every 4 softmax elements use the FMA-pipe exp2 polynomial instead of MUFU.EX2
- * (-1 = built-in default per head_dim, 0 = MUFU only ... 3).  Changes results only below bf16 resolution of P. */
+ * (-1 = built-in default per head_dim, 0 = MUFU only ... 3; 100 / 101 = tail split off / on).  Changes results only below bf16 resolution of P. */
 int fwb_attn_set_tuning(int exp2_poly_quarters);
 
 /* ---- K7: LayerNorm (+affine) (+modulate) -> bf16 ------------------------------------------------------------------

@@ -171,6 +171,37 @@ def test_attention_split_kv_partials_and_merge(fwb):
     torch.testing.assert_close(lse[0], ref_lse, rtol=1e-4, atol=2e-3)
 
 
+@pytest.mark.parametrize("B,H,Lq,Lk,D", [(1, 40, 4095, 8190, 128),      # DiT self-attention shard at 8 ranks, one K|V slice: 640 tiles
+                                         (1, 12, 4095, 32865, 96),      # adapter, video <- geometry, 8 ranks: 192 tiles
+                                         (1, 16, 4695, 32865, 64),      # VGGT global attention shard: 304 tiles
+                                         (3, 16, 1565, 1565, 64),       # VGGT frame attention of a 3-frame shard: 336 tiles
+                                         (1, 2, 300, 5000, 128)])       # fewer tiles than SMs
+def test_attention_tail_split_matches_unsplit(fwb, B, H, Lq, Lk, D):
+    """Tile schedule: the last, partly filled wave of (256-row x head) tiles is split along the keys over the idle SMs and
+    merged.  The result must agree with the unsplit schedule to one bf16 rounding, in the bf16-output and the split-KV
+    (fp32 partial + lse) modes alike."""
+    torch.manual_seed(Lq + Lk + D)
+    q, k, v = (_bf(torch.randn(B, L, H, D, device="cuda")) for L in (Lq, Lk, Lk))
+    part = torch.empty(2, B, Lq, H, D, device="cuda")
+    lse = torch.empty(2, B, H, Lq, device="cuda")
+    try:
+        fwb.lib.fwb_attn_set_tuning(100)           # tail split off
+        ref = fwb.attention(q, k, v)
+        fwb.attention_partial(q, k, v, part[0], lse[0])
+    finally:
+        fwb.lib.fwb_attn_set_tuning(101)
+    out = fwb.attention(q, k, v)
+    fwb.attention_partial(q, k, v, part[1], lse[1])
+    torch.cuda.synchronize()
+    scale = ref.float().abs().max()
+    assert (out.float() - ref.float()).abs().max() <= 2 ** -7 * scale
+    assert (part[1] - part[0]).abs().max() <= 1e-4 * scale
+    torch.testing.assert_close(lse[1], lse[0], rtol=0, atol=1e-4)
+    # and against fp32 math on a slice of the rows (the full score matrix would not fit for the large cases)
+    rows = slice(Lq - 300, Lq)
+    torch.testing.assert_close(out[:, rows].float(), _attn_ref(q[:, rows], k, v), rtol=2e-2, atol=6e-3)
+
+
 def test_attention_softmax_rows_sum_to_one_full_size(fwb):
     """Size-independent property at the BASELINE C2 size (L = 32760 tokens, 128-dim heads): with V = 1 the output is 1."""
     torch.manual_seed(2)
