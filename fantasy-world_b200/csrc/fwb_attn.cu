@@ -512,8 +512,8 @@ static int attn_impl(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_t
                      cudaStream_t stream);
 
 extern "C" size_t fwb_attn_workspace_bytes(void) {
-  // at most one wave of split CTAs: (#SMs) x 256 rows x (128 + 1) floats
-  return (size_t)(num_sms() > 0 ? num_sms() : 148) * 2 * BQ * (128 + 1) * sizeof(float);
+  // up to four rounds of split CTAs: 4 x (#SMs) slots of 256 rows x (128 + 1) floats  (78 MB on a 148-SM part)
+  return (size_t)4 * (num_sms() > 0 ? num_sms() : 148) * 2 * BQ * (128 + 1) * sizeof(float);
 }
 
 extern "C" int fwb_attn_fwd(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v,
@@ -585,19 +585,23 @@ static int attn_impl(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_t
   if (ws && !accumulate && g_attn_tail_split && W > 0 && n_tiles % W != 0) {
     const long long full = (n_tiles / W) * W, tail = n_tiles - full;
     const int n_kv_all = (Lk + BKV - 1) / BKV;
-    long long S = W / tail;
-    if (S > 16) S = 16;
-    if (S > n_kv_all / 4) S = n_kv_all / 4;      // at least 4 KV tiles per split
-    if (S >= 2) {
-      const double plain = (double)(full / W + 1);
-      const double split = (double)(full / W) + 1.0 / (double)S + 0.04;   // + prologue/epilogue of the short CTAs and the merge
-      const size_t need = (size_t)tail * S * 2 * BQ * (D + 1) * sizeof(float);
-      if (split <= 0.95 * plain && need <= ws_bytes && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
-        p.n_full = (int)full;
-        p.S = (int)S;
-        p.ws_out = reinterpret_cast<float*>(ws);
-        p.ws_lse = p.ws_out + (size_t)tail * S * 2 * BQ * D;
+    // S splits per tail tile -> tail * S short CTAs running in ceil(tail * S / W) rounds of 1/S of a full tile each
+    const double plain = (double)(full / W + 1);
+    const long long max_slots = (long long)(ws_bytes / ((size_t)2 * BQ * (D + 1) * sizeof(float)));
+    double best = plain;
+    int best_S = 1;
+    for (int S = 2; S <= 16 && S <= n_kv_all / 4 && tail * S <= max_slots; ++S) {   // at least 4 KV tiles per split
+      const double cost = (double)(full / W) + (double)((tail * S + W - 1) / W) / S + 0.04;   // + short-CTA prologue / merge
+      if (cost < best - 1e-9) {
+        best = cost;
+        best_S = S;
       }
+    }
+    if (best_S >= 2 && best <= 0.93 * plain && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
+      p.n_full = (int)full;
+      p.S = best_S;
+      p.ws_out = reinterpret_cast<float*>(ws);
+      p.ws_lse = p.ws_out + (size_t)tail * best_S * 2 * BQ * D;
     }
   }
   if (D == 64) return launch_attn_emu<64>(g_attn_emu >= 0 ? g_attn_emu : 0, tq, tk, tv, p, B, H, stream);

@@ -195,8 +195,10 @@ def test_attention_tail_split_matches_unsplit(fwb, B, H, Lq, Lk, D):
     torch.cuda.synchronize()
     scale = ref.float().abs().max()
     assert (out.float() - ref.float()).abs().max() <= 2 ** -7 * scale
-    assert (part[1] - part[0]).abs().max() <= 1e-4 * scale
-    torch.testing.assert_close(lse[1], lse[0], rtol=0, atol=1e-4)
+    # P is rounded to bf16 relative to a (stale-tolerant) running row max that differs between the schedules: the fp32 partials
+    # carry that rounding noise (2^-9 per element of P, a few sigma of the resulting sum), far below a bf16 ulp of the output
+    assert (part[1] - part[0]).abs().max() <= 2 ** -8 * scale
+    torch.testing.assert_close(lse[1], lse[0], rtol=0, atol=2e-3)
     # and against fp32 math on a slice of the rows (the full score matrix would not fit for the large cases)
     rows = slice(Lq - 300, Lq)
     torch.testing.assert_close(out[:, rows].float(), _attn_ref(q[:, rows], k, v), rtol=2e-2, atol=6e-3)
