@@ -54,6 +54,29 @@ struct AttnParams {
   float* ws_lse;     // [tail, S, 256]
 };
 
+// Optional timeline instrumentation (tools/attn_trace.py builds a separate library with -DFWB_ATTN_TRACE; never in libfwb200.so):
+// SM clock stamps of one CTA's softmax warps and MMA thread for the first 64 KV tiles.
+#ifdef FWB_ATTN_TRACE
+__device__ long long g_trace[9][64][8];
+__device__ int g_trace_cta = 300;
+__device__ __forceinline__ long long trace_clock() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+  return t;
+}
+#define TRACE(slot, j, ev)                                                                             \
+  do {                                                                                                 \
+    if ((int)blockIdx.x == g_trace_cta && (j) < 64 && lane_id() == 0) g_trace[slot][j][ev] = trace_clock(); \
+  } while (0)
+#define TRACE1(slot, j, ev)                                                                  \
+  do {                                                                                       \
+    if ((int)blockIdx.x == g_trace_cta && (j) < 64) g_trace[slot][j][ev] = trace_clock();    \
+  } while (0)
+#else
+#define TRACE(slot, j, ev) do { } while (0)
+#define TRACE1(slot, j, ev) do { } while (0)
+#endif
+
 template <int D>
 struct AttnCfg {
   static constexpr int kBoxes = D / 64;                   // 64-column TMA boxes per tile
@@ -207,7 +230,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int j = 0; j < n_kv; ++j) {
         const uint32_t vs = j % ST, vph = (j / ST) & 1;
         for (int i = 0; i < 2; ++i) {
+          TRACE1(8, j, i * 3 + 0);
           mbar_wait(&p_full[i], j & 1);
+          TRACE1(8, j, i * 3 + 1);
           if (i == 0) mbar_wait(&v_full[vs], vph);
           tc_fence_after();
           issue_pv(i, vs, j > 0);
@@ -224,6 +249,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           } else {
             tc_commit(&o_full[i]);
           }
+          TRACE1(8, j, i * 3 + 2);
         }
       }
     }
@@ -239,7 +265,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float l_sum = 0.f;
 
     for (int j = 0; j < n_kv; ++j) {
+      TRACE(warp, j, 0);
       mbar_wait(&s_full[i], j & 1);
+      TRACE(warp, j, 1);
       tc_fence_after();
       uint32_t v[128];
       tmem_ld32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
@@ -247,6 +275,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld32(s_tmem + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
       tmem_ld32(s_tmem + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
       tmem_ld_wait();
+      TRACE(warp, j, 2);
 
       if (j == j_ragged) {
         const int valid = p.Lk - (kv0 + j) * BKV;
@@ -284,6 +313,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       }
+      TRACE(warp, j, 3);
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       uint32_t pk[64];
 #pragma unroll
@@ -301,12 +331,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         pk[c / 2 + 1] = pack_bf16x2(p2, p3);
       }
       l_sum += (a0 + a1) + (a2 + a3);
+      TRACE(warp, j, 4);
       tmem_st32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
       tmem_st32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[i]);
+      TRACE(warp, j, 5);
     }
 
     // epilogue: O / l  -> bf16 -> global
@@ -378,10 +410,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
-int make_qkv_map(CUtensorMap* m, const fwb_tensor4_t* t, int B, int H, int L, int D) {
+int make_qkv_map(CUtensorMap* m, const fwb_tensor4_t* t, int B, int H, int L, int D, int box_rows = 128) {
   uint64_t dims[4] = {(uint64_t)D, (uint64_t)H, (uint64_t)L, (uint64_t)B};
   uint64_t str[3] = {(uint64_t)t->sh * 2, (uint64_t)t->sl * 2, (uint64_t)t->sb * 2};
-  uint32_t box[4] = {64, 1, 128, 1};
+  uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
   return make_tmap_bf16(m, t->ptr, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
@@ -450,6 +482,380 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
   return FWB_OK;
 }
 
+
+// =====================================================================================================================
+// attn2: decoupled pipeline.  The v1 kernel above keeps P aliased on S, so QK_i(j+1) can only be issued after PV_i(j): the
+// chain softmax -> P hand-off -> PV + QK -> commit -> wake-up is serial per Q tile (measured with tools/attn_trace.py: the
+// softmax warps wait ~40 % of the time and the tensor pipe idles ~45 %).  Here P_i has its own TMEM columns, the softmax
+// releases S_i as soon as it sits in registers, and each Q tile has its own MMA-issuing warp:
+//   warps 0-3 / 4-7   softmax of Q tile 0 / 1          warp 8 / 9   MMA issuer of Q tile 0 / 1          warp 10   TMA
+//   MMA warp i:  for j: [S_i free] QK_i(j) -> s_full ;  [P_i(j-1) written] PV_i(j-1) -> p_free
+//   softmax i :  for j: [s_full] S -> registers -> s_free ; max / exp2 ; [p_free(j-1)] P -> TMEM -> p_full
+// so QK_i(j+1) runs on the tensor pipe while softmax_i(j) is still computing, and the softmax warps never wait in steady
+// state.  TMEM (512 columns) has to hold O_0 O_1 S_0 P_0 S_1 P_1 = 2 * (D + 1.5 * BKV): head_dim 64 -> BKV 128 (512
+// columns), head_dim 128 -> BKV 64 (448 columns).  K/V stages are released by both MMA warps (mbarrier count 2).
+// =====================================================================================================================
+constexpr int kAttn2Threads = 352;
+__device__ int g_attn2_pingpong = 1;   // exp2 phases of the two Q tiles alternate through named barriers (fwb_attn_set_tuning(1000 / 1001))
+
+template <int D, int BK>
+struct Attn2Cfg {
+  static constexpr int kBoxes = D / 64;
+  static constexpr int kQBoxBytes = BQ * 128;              // one 64-column box of a Q tile
+  static constexpr int kQTileBytes = kBoxes * kQBoxBytes;
+  static constexpr int kKVBoxBytes = BK * 128;             // one 64-column box of a K or V tile
+  static constexpr int kKVTileBytes = kBoxes * kKVBoxBytes;
+  static constexpr int kStages = 4;
+  static constexpr int kSmemBytes = 2 * kQTileBytes + 2 * kStages * kKVTileBytes + 1024;
+  static constexpr uint32_t kColO = 0;                     // O_i at i * D
+  static constexpr uint32_t kColS = 2 * D;                 // S_i at 2D + i * 1.5 BK, P_i right behind S_i
+  static constexpr uint32_t kTileCols = BK + BK / 2;
+  static_assert(2 * D + 2 * kTileCols <= 512, "TMEM overflow");
+};
+
+template <int D, int BK>
+__global__ void __launch_bounds__(kAttn2Threads, 1)
+attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+             const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using Cfg = Attn2Cfg<D, BK>;
+  constexpr int ST = Cfg::kStages;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                     // [2][kQTileBytes]
+  uint8_t* sK = smem + 2 * Cfg::kQTileBytes;              // [ST][kKVTileBytes]
+  uint8_t* sV = sK + ST * Cfg::kKVTileBytes;              // [ST][kKVTileBytes]
+  __shared__ uint64_t q_full[2], k_full[ST], k_empty[ST], v_full[ST], v_empty[ST];
+  __shared__ uint64_t s_full[2], s_free[2], p_full[2], p_free[2], o_full[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float pp_scratch[1 + 256];   // [0] = 0.0f (read behind the ping-pong barrier), [1 + tid] = sink for the block sums
+
+  const uint32_t warp = warp_id_uniform();
+  const uint32_t lane = lane_id();
+  const uint32_t pp_addr = smem_u32(pp_scratch);
+  if (threadIdx.x == 0) pp_scratch[0] = 0.f;
+  auto decode = [&](int& tile, int& split, int& nsplit) {
+    tile = blockIdx.x; split = 0; nsplit = 1;
+    if (tile >= p.n_full) {
+      const int r = tile - p.n_full;
+      tile = p.n_full + r / p.S;
+      split = r % p.S;
+      nsplit = p.S;
+    }
+  };
+  int qblock, head, batch, kv0, n_kv, j_ragged;
+  {
+    int tile, split, nsplit;
+    decode(tile, split, nsplit);
+    qblock = tile % p.nq; head = (tile / p.nq) % p.H; batch = tile / (p.nq * p.H);
+    const int n_kv_all = (p.Lk + BK - 1) / BK;
+    kv0 = (int)((long long)split * n_kv_all / nsplit);
+    n_kv = (int)((long long)(split + 1) * n_kv_all / nsplit) - kv0;
+    j_ragged = n_kv_all - 1 - kv0;
+  }
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);   // one arrive per softmax warp
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_free[i], 1);
+      mbar_init(&o_full[i], 1);
+    }
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 2);  // one commit per MMA warp
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 2);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 8) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 10) {
+    // ------------------------------------ TMA producer ------------------------------------
+    if (elect_one()) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_arrive_expect_tx(&q_full[i], Cfg::kQTileBytes);
+        for (int b = 0; b < Cfg::kBoxes; ++b)
+          tma_load_4d(sQ + i * Cfg::kQTileBytes + b * Cfg::kQBoxBytes, &tmQ, &q_full[i], b * 64, head, (qblock * 2 + i) * BQ,
+                      batch);
+      }
+      for (int j = 0; j < n_kv; ++j) {
+        const uint32_t s = j % ST, ph = (j / ST) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], Cfg::kKVTileBytes);
+        for (int b = 0; b < Cfg::kBoxes; ++b)
+          tma_load_4d(sK + s * Cfg::kKVTileBytes + b * Cfg::kKVBoxBytes, &tmK, &k_full[s], b * 64, head, (kv0 + j) * BK, batch);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], Cfg::kKVTileBytes);
+        for (int b = 0; b < Cfg::kBoxes; ++b)
+          tma_load_4d(sV + s * Cfg::kKVTileBytes + b * Cfg::kKVBoxBytes, &tmV, &v_full[s], b * 64, head, (kv0 + j) * BK, batch);
+      }
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------ MMA issuer of Q tile i ----------------------------
+    if (elect_one()) {
+      const int i = warp - 8;
+      constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BK, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);  // B = V is MN-major (d contiguous)
+      const int ksteps_qk = (p.d_real + 15) / 16;
+      const uint32_t qa = smem_u32(sQ) + i * Cfg::kQTileBytes, k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      const uint32_t s_tmem = tmem_base + Cfg::kColS + i * Cfg::kTileCols;
+      const uint32_t p_tmem = s_tmem + BK;
+      const uint32_t o_tmem = tmem_base + Cfg::kColO + i * D;
+
+      mbar_wait(&q_full[i], 0);
+      for (int j = 0; j <= n_kv; ++j) {
+        if (j < n_kv) {
+          // S_i(j) = Q_i K_j^T  — needs the softmax to have pulled S_i(j-1) into registers
+          const uint32_t ks = j % ST;
+          if (j > 0) mbar_wait(&s_free[i], (j - 1) & 1);
+          mbar_wait(&k_full[ks], (j / ST) & 1);
+          tc_fence_after();
+          const uint32_t ka = k_addr + ks * Cfg::kKVTileBytes;
+          for (int kk = 0; kk < ksteps_qk; ++kk) {
+            umma_ss(s_tmem, make_smem_desc(qa + (kk >> 2) * Cfg::kQBoxBytes + (kk & 3) * 32, 0, 1024, SWZ_128B),
+                    make_smem_desc(ka + (kk >> 2) * Cfg::kKVBoxBytes + (kk & 3) * 32, 0, 1024, SWZ_128B), idesc_qk, kk > 0);
+          }
+          tc_commit(&s_full[i]);
+          tc_commit(&k_empty[ks]);
+          TRACE1(8 + 0, j, i * 3 + 0);
+        }
+        if (j > 0) {
+          // O_i += P_i(j-1) V_(j-1)
+          const int jj = j - 1;
+          const uint32_t vs = jj % ST;
+          mbar_wait(&p_full[i], jj & 1);
+          mbar_wait(&v_full[vs], (jj / ST) & 1);
+          tc_fence_after();
+          const uint32_t va = v_addr + vs * Cfg::kKVTileBytes;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            // 16 kv rows per K-step = 2048 B; LBO = stride between the 64-column d boxes, SBO = 8 kv rows
+            umma_ts(o_tmem, p_tmem + kk * 8, make_smem_desc(va + kk * 2048, Cfg::kKVBoxBytes, 1024, SWZ_128B), idesc_pv,
+                    jj > 0 || kk > 0);
+          }
+          tc_commit(&p_free[i]);
+          tc_commit(&v_empty[vs]);
+          if (jj == n_kv - 1) tc_commit(&o_full[i]);
+          TRACE1(8 + 0, jj, i * 3 + 1);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------ softmax + epilogue ------------------------------
+    const int i = warp >> 2;
+    const uint32_t quad = warp & 3;
+    const uint32_t lane_off = (quad * 32) << 16;
+    const uint32_t s_tmem = tmem_base + Cfg::kColS + i * Cfg::kTileCols + lane_off;
+    const uint32_t p_tmem = s_tmem + BK;
+    const uint32_t o_tmem = tmem_base + Cfg::kColO + i * D + lane_off;
+    const float sl2 = p.scale_log2;
+    float m_used = -INFINITY;
+    float l_sum = 0.f;
+    // MUFU ping-pong.  Warp w (Q tile 0) and warp w+4 (Q tile 1) sit on the same SM sub-partition and share its MUFU
+    // (4 lanes/clk: 8 clk per warp-wide ex2).  Left alone they fall into lock-step: the exp2 phases collide at half rate and
+    // the MUFU idles while both do the row max and the TMEM traffic (tools/attn_trace.py).  Two named barriers per warp pair
+    // make the exp2 phases alternate, so one tile's max / TMEM phase hides under the other's exponentials.
+    const bool pingpong = g_attn2_pingpong != 0;
+    const uint32_t bar_mine = 1 + quad + 4 * i, bar_other = 1 + quad + 4 * (1 - i);
+    if (pingpong && i == 1) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");   // tile 0 goes first
+
+    for (int j = 0; j < n_kv; ++j) {
+      TRACE(warp, j, 0);
+      mbar_wait(&s_full[i], j & 1);
+      TRACE(warp, j, 1);
+      tc_fence_after();
+      uint32_t v[BK];
+#pragma unroll
+      for (int c0 = 0; c0 < BK; c0 += 32) tmem_ld32(s_tmem + c0, *reinterpret_cast<uint32_t(*)[32]>(&v[c0]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[i]);   // S_i is in registers: the MMA warp may overwrite it with S_i(j+1)
+      TRACE(warp, j, 2);
+
+      if (j == j_ragged) {
+        const int valid = p.Lk - (kv0 + j) * BK;
+        if (valid < BK) {
+#pragma unroll
+          for (int c = 0; c < BK; ++c)
+            if (c >= valid) v[c] = 0xFF800000u;  // -inf
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < BK; c += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(v[c]));
+        mx1 = fmaxf(mx1, __uint_as_float(v[c + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(v[c + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(v[c + 3]));
+      }
+      const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
+      const bool need = m_new > m_used + 8.0f;
+      bool p_free_seen = false;
+      if (__any_sync(0xffffffffu, need)) {
+        const float m_next = fmaxf(m_used, m_new);
+        const float alpha = fast_exp2(m_used - m_next);
+        l_sum *= alpha;
+        m_used = m_next;
+        if (j > 0) {
+          mbar_wait(&p_free[i], (j - 1) & 1);   // PV_i(j-1) has completed: O_i is quiescent
+          p_free_seen = true;
+          tc_fence_after();
+#pragma unroll
+          for (int c0 = 0; c0 < D; c0 += 16) {
+            uint32_t o[16];
+            tmem_ld16(o_tmem + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+            tmem_st16(o_tmem + c0, o);
+          }
+        }
+      }
+      // m_used is threaded through the barrier asm so that the exponentials (register-only math, which the compiler may
+      // otherwise move across an asm volatile) stay behind it; same for the accumulators and the arrive below
+      if (pingpong) {
+        // ptxas moves register-only math (the exponentials) freely across a BAR; a volatile shared-memory load behind the
+        // barrier that feeds m_used (+0) and a volatile store of the sums in front of the arrive pin the exp2 phase
+        float z;
+        asm volatile("bar.sync %1, 64;\n\tld.volatile.shared.f32 %0, [%2];" : "=f"(z) : "r"(bar_mine), "r"(pp_addr) : "memory");
+        m_used += z;
+      }
+      TRACE(warp, j, 3);
+      // (a software-pipelined variant that ties the consumers of chunk k-1 behind the MUFUs of chunk k runs at 9.7 instead of
+      // 12.3 clk per element in isolation (tools/ubench/mufu.cu) but made no difference inside the kernel; not kept)
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      uint32_t pk[BK / 2];
+#pragma unroll
+      for (int c = 0; c < BK; c += 4) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(v[c]), sl2, -m_used));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), sl2, -m_used));
+        const float p2 = fast_exp2(fmaf(__uint_as_float(v[c + 2]), sl2, -m_used));
+        const float p3 = fast_exp2(fmaf(__uint_as_float(v[c + 3]), sl2, -m_used));
+        a0 += p0; a1 += p1; a2 += p2; a3 += p3;
+        pk[c / 2] = pack_bf16x2(p0, p1);
+        pk[c / 2 + 1] = pack_bf16x2(p2, p3);
+      }
+      const float blk_sum = (a0 + a1) + (a2 + a3);
+      if (pingpong)
+        asm volatile("st.volatile.shared.f32 [%0], %1;\n\tbar.arrive %2, 64;" ::"r"(pp_addr + 4 + 4 * threadIdx.x), "f"(blk_sum),
+                     "r"(bar_other)
+                     : "memory");
+      l_sum += blk_sum;
+      TRACE(warp, j, 4);
+      if (j > 0 && !p_free_seen) {
+        mbar_wait(&p_free[i], (j - 1) & 1);     // PV_i(j-1) has finished reading P_i
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int c0 = 0; c0 < BK / 2; c0 += 32) tmem_st32(p_tmem + c0, *reinterpret_cast<uint32_t(*)[32]>(&pk[c0]));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[i]);
+      TRACE(warp, j, 5);
+    }
+
+    if (pingpong && i == 0) asm volatile("bar.sync %0, 64;" ::"r"(bar_mine) : "memory");   // absorb tile 1's last arrive
+
+    // epilogue: O / l  -> bf16 -> global (or fp32 partial / workspace, as in v1)
+    mbar_wait(&o_full[i], 0);
+    tc_fence_after();
+    const int row = (qblock * 2 + i) * BQ + quad * 32 + lane;
+    const float inv_l = 1.f / l_sum;
+    __nv_bfloat16* orow = p.out + (long long)batch * p.o_sb + (long long)row * p.o_sl + (long long)head * p.o_sh;
+    const int row_in_tile = i * BQ + quad * 32 + lane;
+    float* ws_row = nullptr;
+    int tile, split, nsplit;
+    decode(tile, split, nsplit);
+    if (nsplit > 1) {
+      const long long slot = (long long)(tile - p.n_full) * p.S + split;
+      ws_row = p.ws_out + (slot * (2 * BQ) + row_in_tile) * p.d_real;
+      p.ws_lse[slot * (2 * BQ) + row_in_tile] = m_used + log2f(l_sum);
+    } else if (p.part_lse && row < p.Lq) {
+      p.part_lse[((long long)batch * p.H + head) * p.Lq + row] = m_used + log2f(l_sum);
+    }
+#pragma unroll
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t o[32];
+      tmem_ld32(o_tmem + c0, o);
+      tmem_ld_wait();
+      float* frow = ws_row ? ws_row : (p.part_out ? p.part_out + (((long long)batch * p.Lq + row) * p.H + head) * p.d_real : nullptr);
+      if (frow) {
+        if ((ws_row || row < p.Lq) && c0 < p.d_real) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4)
+            *reinterpret_cast<float4*>(frow + c0 + c) =
+                make_float4(__uint_as_float(o[c]) * inv_l, __uint_as_float(o[c + 1]) * inv_l, __uint_as_float(o[c + 2]) * inv_l,
+                            __uint_as_float(o[c + 3]) * inv_l);
+        }
+      } else if (row < p.Lq && c0 < p.d_real) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          float y[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) y[t] = __uint_as_float(o[c + t]) * inv_l;
+          if (p.accumulate) {
+            const uint4 prev = *reinterpret_cast<const uint4*>(orow + c0 + c);
+            const uint32_t pw[4] = {prev.x, prev.y, prev.z, prev.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              y[2 * t] = bf16_round(y[2 * t]) + __uint_as_float(pw[t] << 16);
+              y[2 * t + 1] = bf16_round(y[2 * t + 1]) + __uint_as_float(pw[t] & 0xFFFF0000u);
+            }
+          }
+          uint4 w;
+          w.x = pack_bf16x2(y[0], y[1]);
+          w.y = pack_bf16x2(y[2], y[3]);
+          w.z = pack_bf16x2(y[4], y[5]);
+          w.w = pack_bf16x2(y[6], y[7]);
+          *reinterpret_cast<uint4*>(orow + c0 + c) = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+template <int D, int BK>
+int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B, int H,
+                 cudaStream_t stream) {
+  using Cfg = Attn2Cfg<D, BK>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FWB_CUDA(cudaFuncSetAttribute(attn2_kernel<D, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const long long n_tiles = (long long)p.nq * H * B;
+  const long long tail = n_tiles - p.n_full;
+  const long long grid = p.n_full + (p.S > 1 ? tail * p.S : tail);
+  FWB_CHECK(grid < (1ll << 31), "attn: grid too large");
+  attn2_kernel<D, BK><<<(unsigned)grid, kAttn2Threads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  FWB_CUDA(cudaGetLastError());
+  if (p.S > 1) {
+    const long long total = tail * (2 * BQ) * (p.d_real / 8);
+    attn_tail_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, (int)tail);
+    FWB_CUDA(cudaGetLastError());
+  }
+  return FWB_OK;
+}
+
 template <int D>
 int launch_attn_emu(int emu, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
                     int H, cudaStream_t stream) {
@@ -492,13 +898,36 @@ __global__ void attn_merge_kernel(const float* __restrict__ part, const float* _
   *reinterpret_cast<uint4*>(out + b * o_sb + l * o_sl + h * o_sh + pc * 8) = o;
 }
 
+int g_attn_variant = 0;     // 0: per head_dim default (64 -> attn2, 96 / 128 -> v1: measured), 1: v1 kernel, 2: decoupled attn2
+                            // kernel.  fwb_attn_set_tuning(200 / 201 / 202) selects.
 int g_attn_tail_split = 1;  // fwb_attn_set_tuning(100 / 101) turns the tail split off / on (A/B measurements)
 int g_attn_emu = -1;  // -1: default (0: measured fastest on B200, the softmax is issue-bound not MUFU-bound); 0..3: number of
                       // softmax elements out of every 4 that use exp2_poly
 
 }  // namespace
 
+#ifdef FWB_ATTN_TRACE
+extern "C" int fwb_attn_trace_read(long long* host_out, int cta) {
+  if (cta >= 0) {
+    FWB_CUDA(cudaMemcpyToSymbol(g_trace_cta, &cta, sizeof(int)));
+    return FWB_OK;
+  }
+  FWB_CUDA(cudaDeviceSynchronize());
+  FWB_CUDA(cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 9 * 64 * 8));
+  return FWB_OK;
+}
+#endif
+
 extern "C" int fwb_attn_set_tuning(int exp2_poly_quarters) {
+  if (exp2_poly_quarters >= 1000 && exp2_poly_quarters < 100000) {
+    const int clk = exp2_poly_quarters - 1000;
+    FWB_CUDA(cudaMemcpyToSymbol(g_attn2_pingpong, &clk, sizeof(int)));
+    return FWB_OK;
+  }
+  if (exp2_poly_quarters >= 200 && exp2_poly_quarters <= 202) {
+    g_attn_variant = exp2_poly_quarters - 200;
+    return FWB_OK;
+  }
   if (exp2_poly_quarters == 100 || exp2_poly_quarters == 101) {
     g_attn_tail_split = exp2_poly_quarters - 100;
     return FWB_OK;
@@ -561,8 +990,10 @@ static int attn_impl(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_t
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = make_qkv_map(&tq, q, B, H, Lq, D))) return rc;
-  if ((rc = make_qkv_map(&tk, k, B, H, Lk, D))) return rc;
-  if ((rc = make_qkv_map(&tv, v, B, H, Lk, D))) return rc;
+  const int variant = g_attn_variant ? g_attn_variant : (D == 64 ? 2 : 1);
+  const int bk = (variant == 2) ? (D == 64 ? 128 : 64) : BKV;     // keys per KV tile of the kernel that will run
+  if ((rc = make_qkv_map(&tk, k, B, H, Lk, D, bk))) return rc;
+  if ((rc = make_qkv_map(&tv, v, B, H, Lk, D, bk))) return rc;
   AttnParams p;
   p.out = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(out->ptr));
   p.o_sb = out->sb; p.o_sl = out->sl; p.o_sh = out->sh;
@@ -584,13 +1015,14 @@ static int attn_impl(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_t
   const int W = num_sms();
   if (ws && !accumulate && g_attn_tail_split && W > 0 && n_tiles % W != 0) {
     const long long full = (n_tiles / W) * W, tail = n_tiles - full;
-    const int n_kv_all = (Lk + BKV - 1) / BKV;
+    const int n_kv_all = (Lk + bk - 1) / bk;
+    const int max_S = Lk / 512;                       // at least 512 keys per split
     // S splits per tail tile -> tail * S short CTAs running in ceil(tail * S / W) rounds of 1/S of a full tile each
     const double plain = (double)(full / W + 1);
     const long long max_slots = (long long)(ws_bytes / ((size_t)2 * BQ * (D + 1) * sizeof(float)));
     double best = plain;
     int best_S = 1;
-    for (int S = 2; S <= 16 && S <= n_kv_all / 4 && tail * S <= max_slots; ++S) {   // at least 4 KV tiles per split
+    for (int S = 2; S <= 16 && S <= max_S && S <= n_kv_all && tail * S <= max_slots; ++S) {
       const double cost = (double)(full / W) + (double)((tail * S + W - 1) / W) / S + 0.04;   // + short-CTA prologue / merge
       if (cost < best - 1e-9) {
         best = cost;
@@ -603,6 +1035,10 @@ static int attn_impl(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_t
       p.ws_out = reinterpret_cast<float*>(ws);
       p.ws_lse = p.ws_out + (size_t)tail * best_S * 2 * BQ * D;
     }
+  }
+  if (variant == 2) {
+    if (D == 64) return launch_attn2<64, 128>(tq, tk, tv, p, B, H, stream);
+    return launch_attn2<128, 64>(tq, tk, tv, p, B, H, stream);
   }
   if (D == 64) return launch_attn_emu<64>(g_attn_emu >= 0 ? g_attn_emu : 0, tq, tk, tv, p, B, H, stream);
   return launch_attn_emu<128>(g_attn_emu >= 0 ? g_attn_emu : 0, tq, tk, tv, p, B, H, stream);

@@ -204,6 +204,31 @@ def test_attention_tail_split_matches_unsplit(fwb, B, H, Lq, Lk, D):
     torch.testing.assert_close(out[:, rows].float(), _attn_ref(q[:, rows], k, v), rtol=2e-2, atol=6e-3)
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("B,H,Lq,Lk,D", [(1, 3, 1000, 777, 128), (2, 4, 300, 1300, 64), (1, 12, 1560, 1565, 96), (1, 2, 129, 1, 128),
+                                         (1, 8, 4095, 8190, 128), (3, 16, 1565, 1565, 64)])
+def test_attention_kernel_variants(fwb, variant, B, H, Lq, Lk, D):
+    """Both attention kernels (v1: P aliased on S, one MMA thread; attn2: decoupled S / P, one MMA warp per Q tile, MUFU
+    ping-pong) against fp32 math, including the split-KV outputs.  The default picks one per head_dim; both stay covered."""
+    torch.manual_seed(variant * 7 + Lq + Lk + D)
+    q, k, v = (_bf(torch.randn(B, L, H, D, device="cuda")) for L in (Lq, Lk, Lk))
+    part = torch.empty(1, B, Lq, H, D, device="cuda")
+    lse = torch.empty(1, B, H, Lq, device="cuda")
+    try:
+        fwb.lib.fwb_attn_set_tuning(200 + variant)
+        out = fwb.attention(q, k, v)
+        fwb.attention_partial(q, k, v, part[0], lse[0])
+        merged = fwb.attention_merge(part, lse)
+        torch.cuda.synchronize()
+    finally:
+        fwb.lib.fwb_attn_set_tuning(200)
+    ref = _attn_ref(q, k, v)
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=6e-3)
+    torch.testing.assert_close(merged.float(), ref, rtol=2e-2, atol=6e-3)
+    s = (q.float().permute(0, 2, 1, 3) @ k.float().permute(0, 2, 3, 1)) / math.sqrt(D)
+    torch.testing.assert_close(lse[0], torch.logsumexp(s, dim=-1) / math.log(2), rtol=1e-4, atol=2e-3)
+
+
 def test_attention_softmax_rows_sum_to_one_full_size(fwb):
     """Size-independent property at the BASELINE C2 size (L = 32760 tokens, 128-dim heads): with V = 1 the output is 1."""
     torch.manual_seed(2)
