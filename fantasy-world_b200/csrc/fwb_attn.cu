@@ -17,6 +17,8 @@
 // the exponentials of a tile cost ~1024 clk of MUFU per SM sub-partition whatever the thread count), P handed over in
 // four 32-key chunks (v3, slower: four mbarrier wake-ups per tile on the MMA thread cost more than the overlap buys),
 // FMA-pipe exp2 polynomial for 25-75 % of the elements (slower: the softmax warps are issue/latency bound, not MUFU bound).
+// A second kernel (attn2, further down) decouples S and P in TMEM and is the default at head_dim 64; both share the tile schedule
+// with the key-split tail (attn_tail_merge_kernel) and the split-KV partial outputs.
 // head_dim 96 (adapter) runs on the D=128 instance: TMA zero-fills columns 96..127 and QK^T skips the dead K-steps.
 // Roofline: tensor-pipe bound, 4*B*H*Lq*Lk*D FLOP.
 #include <math.h>
