@@ -79,6 +79,8 @@ __device__ __forceinline__ long long trace_clock() {
 #define TRACE1(slot, j, ev) do { } while (0)
 #endif
 
+__device__ int g_attn1_pingpong = 0;   // v1 kernel: MUFU ping-pong of the two Q tiles' exp2 phases (fwb_attn_set_tuning(1002 / 1003))
+
 template <int D>
 struct AttnCfg {
   static constexpr int kBoxes = D / 64;                   // 64-column TMA boxes per tile
@@ -117,9 +119,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sV = sK + ST * Cfg::kTileBytes;              // [ST][kTileBytes]
   __shared__ uint64_t q_full[2], k_full[ST], k_empty[ST], v_full[ST], v_empty[ST], s_full[2], p_full[2], o_full[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float pp_scratch[1 + 256];   // MUFU ping-pong pins (see attn2_kernel)
 
   const uint32_t warp = warp_id_uniform();
   const uint32_t lane = lane_id();
+  const uint32_t pp_addr = smem_u32(pp_scratch);
+  if (threadIdx.x == 0) pp_scratch[0] = 0.f;
   // tile schedule (see AttnParams): decoded from blockIdx wherever it is needed instead of being kept live across the KV loop
   auto decode = [&](int& tile, int& split, int& nsplit) {
     tile = blockIdx.x; split = 0; nsplit = 1;
@@ -265,6 +270,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float sl2 = p.scale_log2;
     float m_used = -INFINITY;  // running (stale-tolerant) row max in scaled log2 units
     float l_sum = 0.f;
+    // optional MUFU ping-pong between warp w (Q tile 0) and warp w+4 (Q tile 1), as in attn2_kernel
+    const bool pingpong = g_attn1_pingpong != 0;
+    const uint32_t bar_mine = 1 + quad + 4 * i, bar_other = 1 + quad + 4 * (1 - i);
+    if (pingpong && i == 1) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");
 
     for (int j = 0; j < n_kv; ++j) {
       TRACE(warp, j, 0);
@@ -287,6 +296,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (c >= valid) v[c] = 0xFF800000u;  // -inf
         }
       }
+      // (8 independent max chains instead of 4 measured no shorter: the phase is not bound by the FMNMX3 dependency chain)
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 128; c += 4) {
@@ -316,6 +326,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       TRACE(warp, j, 3);
+      if (pingpong) {
+        float z;
+        asm volatile("bar.sync %1, 64;\n\tld.volatile.shared.f32 %0, [%2];" : "=f"(z) : "r"(bar_mine), "r"(pp_addr) : "memory");
+        m_used += z;
+      }
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       uint32_t pk[64];
 #pragma unroll
@@ -332,7 +347,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         pk[c / 2] = pack_bf16x2(p0, p1);
         pk[c / 2 + 1] = pack_bf16x2(p2, p3);
       }
-      l_sum += (a0 + a1) + (a2 + a3);
+      const float blk_sum = (a0 + a1) + (a2 + a3);
+      if (pingpong)
+        asm volatile("st.volatile.shared.f32 [%0], %1;\n\tbar.arrive %2, 64;" ::"r"(pp_addr + 4 + 4 * threadIdx.x), "f"(blk_sum),
+                     "r"(bar_other)
+                     : "memory");
+      l_sum += blk_sum;
       TRACE(warp, j, 4);
       tmem_st32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
       tmem_st32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
@@ -342,6 +362,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (lane == 0) mbar_arrive(&p_full[i]);
       TRACE(warp, j, 5);
     }
+
+    if (pingpong && i == 0) asm volatile("bar.sync %0, 64;" ::"r"(bar_mine) : "memory");   // absorb tile 1's last arrive
 
     // epilogue: O / l  -> bf16 -> global
     mbar_wait(&o_full[i], 0);
@@ -922,8 +944,12 @@ extern "C" int fwb_attn_trace_read(long long* host_out, int cta) {
 
 extern "C" int fwb_attn_set_tuning(int exp2_poly_quarters) {
   if (exp2_poly_quarters >= 1000 && exp2_poly_quarters < 100000) {
-    const int clk = exp2_poly_quarters - 1000;
-    FWB_CUDA(cudaMemcpyToSymbol(g_attn2_pingpong, &clk, sizeof(int)));
+    const int clk = (exp2_poly_quarters - 1000) & 1;
+    if (exp2_poly_quarters - 1000 >= 2) {
+      FWB_CUDA(cudaMemcpyToSymbol(g_attn1_pingpong, &clk, sizeof(int)));
+    } else {
+      FWB_CUDA(cudaMemcpyToSymbol(g_attn2_pingpong, &clk, sizeof(int)));
+    }
     return FWB_OK;
   }
   if (exp2_poly_quarters >= 200 && exp2_poly_quarters <= 202) {

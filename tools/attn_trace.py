@@ -34,6 +34,8 @@ def run():
     lib.fwb_attn_set_tuning.argtypes = [C.c_int]
     variant = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     lib.fwb_attn_set_tuning(200 + variant)
+    if len(sys.argv) > 3:
+        lib.fwb_attn_set_tuning(int(sys.argv[3]))
     lib.fwb_last_error.restype = C.c_char_p
     out_lines = []
     for (B, H, L, D) in [(1, 40, 32760, 128), (1, 16, 32865, 64)]:
@@ -79,7 +81,7 @@ def run():
         out_lines.append(f"phase: tile1 S_ready minus tile0 S_ready = {float((tr[4, js, 1] - tr[0, js, 1]).float().mean()):.0f} clk")
     text = "\n".join(out_lines)
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
-    (ROOT / "gpurun_out" / f"attn_trace_v{variant}.txt").write_text(text + "\n")
+    (ROOT / "gpurun_out" / f"attn_trace_v{variant}{'_' + sys.argv[3] if len(sys.argv) > 3 else ''}.txt").write_text(text + "\n")
     print(text)
 
 
