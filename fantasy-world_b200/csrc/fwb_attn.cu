@@ -928,7 +928,41 @@ int g_attn_tail_split = 1;  // fwb_attn_set_tuning(100 / 101) turns the tail spl
 int g_attn_emu = -1;  // -1: default (0: measured fastest on B200, the softmax is issue-bound not MUFU-bound); 0..3: number of
                       // softmax elements out of every 4 that use exp2_poly
 
+// Tile schedule planner (pure host arithmetic).  n_tiles tiles on W SMs (one CTA per SM): the first floor(n/W)*W tiles run
+// unsplit; each of the `tail` remaining tiles may be split S ways along the keys -> tail * S short CTAs running in
+// ceil(tail * S / W) rounds of 1/S of a full tile each.  Chooses the S in 2..16 (at least 512 keys per split, slots must fit the
+// workspace) with the smallest modelled time and uses it only for a predicted gain of at least 7 %.
+void attn_plan(long long n_tiles, int Lk, int D, size_t ws_bytes, int W, int* n_full, int* S_out) {
+  *n_full = (int)n_tiles;
+  *S_out = 1;
+  if (W <= 0 || n_tiles % W == 0) return;
+  const long long full = (n_tiles / W) * W, tail = n_tiles - full;
+  const int max_S = Lk / 512;
+  const double plain = (double)(full / W + 1);
+  const long long max_slots = (long long)(ws_bytes / ((size_t)2 * BQ * (D + 1) * sizeof(float)));
+  double best = plain;
+  int best_S = 1;
+  for (int S = 2; S <= 16 && S <= max_S && tail * S <= max_slots; ++S) {
+    const double cost = (double)(full / W) + (double)((tail * S + W - 1) / W) / S + 0.04;   // + short-CTA prologue / merge
+    if (cost < best - 1e-9) {
+      best = cost;
+      best_S = S;
+    }
+  }
+  if (best_S >= 2 && best <= 0.93 * plain) {
+    *n_full = (int)full;
+    *S_out = best_S;
+  }
+}
+
 }  // namespace
+
+extern "C" int fwb_attn_plan(int B, int H, int Lq, int Lk, int D, size_t workspace_bytes, int n_sms, int* n_unsplit_tiles,
+                             int* key_splits) {
+  FWB_CHECK(B > 0 && H > 0 && Lq > 0 && Lk > 0 && n_unsplit_tiles && key_splits, "attn_plan: bad arguments");
+  attn_plan((long long)((Lq + 2 * BQ - 1) / (2 * BQ)) * H * B, Lk, D, workspace_bytes, n_sms, n_unsplit_tiles, key_splits);
+  return FWB_OK;
+}
 
 #ifdef FWB_ATTN_TRACE
 extern "C" int fwb_attn_trace_read(long long* host_out, int cta) {
@@ -1040,28 +1074,14 @@ static int attn_impl(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_t
   p.S = 1;
   p.ws_out = nullptr;
   p.ws_lse = nullptr;
-  const int W = num_sms();
-  if (ws && !accumulate && g_attn_tail_split && W > 0 && n_tiles % W != 0) {
-    const long long full = (n_tiles / W) * W, tail = n_tiles - full;
-    const int n_kv_all = (Lk + bk - 1) / bk;
-    const int max_S = Lk / 512;                       // at least 512 keys per split
-    // S splits per tail tile -> tail * S short CTAs running in ceil(tail * S / W) rounds of 1/S of a full tile each
-    const double plain = (double)(full / W + 1);
-    const long long max_slots = (long long)(ws_bytes / ((size_t)2 * BQ * (D + 1) * sizeof(float)));
-    double best = plain;
-    int best_S = 1;
-    for (int S = 2; S <= 16 && S <= max_S && S <= n_kv_all && tail * S <= max_slots; ++S) {
-      const double cost = (double)(full / W) + (double)((tail * S + W - 1) / W) / S + 0.04;   // + short-CTA prologue / merge
-      if (cost < best - 1e-9) {
-        best = cost;
-        best_S = S;
-      }
-    }
-    if (best_S >= 2 && best <= 0.93 * plain && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
-      p.n_full = (int)full;
-      p.S = best_S;
+  if (ws && !accumulate && g_attn_tail_split && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
+    int n_full = 0, S = 1;
+    attn_plan(n_tiles, Lk, D, ws_bytes, num_sms(), &n_full, &S);
+    if (S >= 2) {
+      p.n_full = n_full;
+      p.S = S;
       p.ws_out = reinterpret_cast<float*>(ws);
-      p.ws_lse = p.ws_out + (size_t)tail * best_S * 2 * BQ * D;
+      p.ws_lse = p.ws_out + (size_t)(n_tiles - n_full) * S * 2 * BQ * D;
     }
   }
   if (variant == 2) {

@@ -66,6 +66,7 @@ def _load():
     lib.fwb_last_error.restype = C.c_char_p
     lib.fwb_attn_workspace_bytes.restype = C.c_size_t
     lib.fwb_attn_workspace_bytes.argtypes = []
+    lib.fwb_attn_plan.argtypes = [i32, i32, i32, i32, i32, C.c_size_t, i32, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     return lib
 
 

@@ -89,6 +89,9 @@ typedef struct {
  * wave are split along the keys over the idle SMs and merged (same result up to one rounding of the merge weights).  This is
  * what keeps the sequence-parallel shards (Lq = L / ranks) from losing up to a full wave per attention. */
 size_t fwb_attn_workspace_bytes(void);
+/* The schedule fwb_attn_fwd would choose (pure host arithmetic, no device needed): how many tiles run unsplit and into how many
+ * key splits each remaining tile is cut (1 = no split), for n_sms SMs and a workspace of workspace_bytes. */
+int fwb_attn_plan(int B, int H, int Lq, int Lk, int D, size_t workspace_bytes, int n_sms, int* n_unsplit_tiles, int* key_splits);
 int fwb_attn_fwd(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_tensor4_t* v, const fwb_tensor4_t* out, int B,
                  int H, int Lq, int Lk, int D, float scale, int accumulate, void* workspace, size_t workspace_bytes,
                  fwb_stream_t stream);

@@ -67,3 +67,44 @@ def test_mirror_state_dict_schema_matches_reference():
     mine = {k: list(v.shape) for k, v in m.state_dict().items()}
     assert mine == schema
     assert isinstance(m.pipe.dit.blocks[1], nn.Identity) and isinstance(agg.global_blocks[0], nn.Identity)
+
+
+def test_attention_tile_schedule_planner():
+    """fwb_attn_plan is pure host arithmetic (no device): the tail split must leave the 1-GPU BASELINE shapes alone, split the
+    sequence-parallel shard shapes, and always fit the workspace."""
+    import ctypes as C
+    import fwb200
+    lib = fwb200.lib
+    ws = int(4 * 148 * 256 * 129 * 4)                     # fwb_attn_workspace_bytes() on a 148-SM part
+
+    def plan(B, H, Lq, Lk, D, ws_bytes=ws, sms=148):
+        n_full, S = C.c_int(), C.c_int()
+        assert lib.fwb_attn_plan(B, H, Lq, Lk, D, ws_bytes, sms, C.byref(n_full), C.byref(S)) == 0
+        n_tiles = -(-Lq // 256) * H * B
+        tail = n_tiles - n_full.value
+        assert 0 <= n_full.value <= n_tiles and n_full.value % sms == 0 or S.value == 1
+        if S.value > 1:
+            assert 2 <= S.value <= 16 and Lk // S.value >= 512
+            assert tail * S.value * 256 * (D + 1) * 4 <= ws_bytes
+        else:
+            assert n_full.value == n_tiles
+        return n_tiles, n_full.value, S.value
+
+    # 1 GPU, C2: DiT self-attention, adapter (both directions), VGGT global / frame, text cross-attention: unsplit
+    for shape in [(1, 40, 32760, 32760, 128), (1, 12, 32760, 32865, 96), (1, 12, 32865, 32760, 96), (1, 16, 32865, 32865, 64),
+                  (21, 16, 1565, 1565, 64), (1, 40, 32760, 512, 128), (1, 40, 32760, 257, 128)]:
+        assert plan(*shape)[2] == 1, shape
+    # 8 ranks: one K|V slice of the DiT self-attention (640 tiles = 4 waves + 48), adapter, VGGT global
+    assert plan(1, 40, 4095, 8190, 128) == (640, 592, 3)
+    n, full, S = plan(1, 12, 4095, 32865, 96)
+    assert (n, full) == (192, 148) and S >= 3
+    n, full, S = plan(1, 12, 4695, 32760, 96)
+    assert (n, full) == (228, 148) and S >= 3
+    n, full, S = plan(1, 16, 4695, 32865, 64)
+    assert (n, full) == (304, 296) and S == 16
+    # fewer tiles than SMs and long keys: everything is split; short keys: never
+    assert plan(1, 2, 300, 5000, 128)[1:] == (0, 9)
+    assert plan(1, 2, 300, 600, 128)[2] == 1
+    # no workspace -> no split; tile count a multiple of the SM count -> no split
+    assert plan(1, 40, 4095, 8190, 128, ws_bytes=0)[2] == 1
+    assert plan(1, 37, 1024, 8192, 128)[2] == 1           # 4 * 37 = 148 tiles
