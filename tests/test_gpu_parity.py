@@ -72,11 +72,11 @@ def test_irg_block_config1_vs_golden_and_oracle(model):
     pos = model.vggt.aggregator._positions(f, h, w, torch.device(dev))
     bf = torch.bfloat16
 
-    def run_gpu():
+    def run_gpu(uncond=False):
         with torch.no_grad():
             return model.IRGBlock[0](x_dit=x_dit.to(dev, bf), x_agg=x_agg.to(dev, bf), context=context.to(dev, bf),
                                      t_mod=t_mod.to(dev, bf), freqs=fr, freqs_dit=fd, freqs_agg=fa, pos=pos, e0=e0.to(dev),
-                                     uncond=False, plucker_fea=plucker.to(dev, bf), plucker_context_lens=torch.ones(1, dtype=torch.long))
+                                     uncond=uncond, plucker_fea=plucker.to(dev, bf), plucker_context_lens=torch.ones(1, dtype=torch.long))
 
     # (ii) against the reference's fp32 (no-autocast) output, with the same fp32 RoPE angles: bf16-sized error
     E.ROPE2D_FP32_ANGLES = True
@@ -99,6 +99,15 @@ def test_irg_block_config1_vs_golden_and_oracle(model):
     assert rel_err(xa2.cpu(), oa) < 1e-2, rel_err(xa2.cpu(), oa)
     # never (much) less accurate than the emulated-bf16 reference itself (fp32-angle run vs fp32-angle emulation)
     assert rel_err(xd.cpu(), g["x_dit_out"]) < 1.5 * rel_err(od, g["x_dit_out"]) + 5e-3
+    # uncond=True: the adapter is skipped (fusion/layer/block.py:70-72); own golden from the reference
+    gu = gold("irg_block_c1_uncond.pt")
+    E.ROPE2D_FP32_ANGLES = True
+    try:
+        xdu, xau, _ = run_gpu(uncond=True)
+    finally:
+        E.ROPE2D_FP32_ANGLES = False
+    assert rel_err(xdu.cpu(), gu["x_dit_out"]) < 2e-2, rel_err(xdu.cpu(), gu["x_dit_out"])
+    assert rel_err(xau.cpu(), gu["x_agg_out"]) < 2e-2, rel_err(xau.cpu(), gu["x_agg_out"])
 
 
 def test_joint_forward_with_heads_vs_golden(model, fp32_rope_angles):

@@ -35,6 +35,12 @@ def test_irg_block_config1():
     xd, xa, _ = O.irg_block(sd, "IRGBlock.0", x_dit, x_agg, context, t_mod, tab, tab_d, tab_a, pos, e0, plucker)
     assert rel_err(xd, g["x_dit_out"]) < TOL, rel_err(xd, g["x_dit_out"])
     assert rel_err(xa, g["x_agg_out"]) < TOL, rel_err(xa, g["x_agg_out"])
+    # uncond=True (fusion/layer/block.py:70-72): the bidirectional adapter is skipped; same inputs, own reference golden
+    gu = gold("irg_block_c1_uncond.pt")
+    xd, xa, _ = O.irg_block(sd, "IRGBlock.0", x_dit, x_agg, context, t_mod, tab, tab_d, tab_a, pos, e0, plucker, uncond=True)
+    assert rel_err(xd, gu["x_dit_out"]) < TOL, rel_err(xd, gu["x_dit_out"])
+    assert rel_err(xa, gu["x_agg_out"]) < TOL, rel_err(xa, gu["x_agg_out"])
+    assert rel_err(gu["x_dit_out"], g["x_dit_out"]) > 1e-2     # the two branches really differ with the synthetic gammas
 
 
 def _inputs(g):
