@@ -143,6 +143,7 @@ def cpu_sample(f=1, h=30, w=52, text_len=512, reps=1):
     plucker = torch.randn(1, L, 2048, generator=g)
     tab, tab_d, tab_a = O.rope_table_3d(128, f, h, w), O.rope_table_3d(96, f, h, w), O.rope_table_3d_with_extra(96, f, h, w, 5)
     _, pos = O.aggregator_input(sd, "vggt.aggregator", torch.zeros(1, f, h, w, 1024))
+    O.USE_TORCH_SDPA = True      # time what the reference runs on CPU (F.scaled_dot_product_attention), not the explicit restatement
     t0 = time.perf_counter()
     with torch.no_grad():
         for _ in range(reps):
@@ -150,6 +151,7 @@ def cpu_sample(f=1, h=30, w=52, text_len=512, reps=1):
             tk = O.vggt_block(sd, "vggt.aggregator.frame_blocks.0", tok, pos, e0)
             O.irg_block(sd, "IRGBlock.0", x1, tk, ctx, t_mod, tab, tab_d, tab_a, pos, e0, plucker)
     dt = (time.perf_counter() - t0) / reps
+    O.USE_TORCH_SDPA = False
     # the oracle recomputes the context K/V inside every block (as the reference does): count them
     extra_kv = 2 * 2 * (text_len + 257) * 5120 * 5120 * 2 + 2 * 2 * L * 2048 * 2048
     flops = forward_flops(f, h, w, 1, 1, text_len) - 2 * L * 5120 * 1024 + extra_kv
@@ -321,6 +323,8 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu_baseline:
         dt, cfl, desc = cpu_sample()
+        if dt < 6.0:                                     # fast host: take a larger sample (10-30 s of CPU work)
+            dt, cfl, desc = cpu_sample(f=min(4, int(12.0 / dt) + 1))
         rate = cfl / dt
         cpu = {"value": rate / (2 * fwd_fl), "unit": "steps/s", "cores": usable_cores(), "kind": "port", "sample": desc,
                "sample_seconds": dt, "achieved_tflops": rate / 1e12}

@@ -66,9 +66,15 @@ def rms_norm(x, w, eps, nm=FP32):
     return nm.r(nm.r(y) * nm.r(w.float()))
 
 
+USE_TORCH_SDPA = False   # bench.py's timed CPU legs set this: call F.scaled_dot_product_attention (what the reference itself calls
+                         # on CPU, wan_video_dit.py:60-65) instead of the explicit restatement below; fp32 mode only
+
+
 def sdpa(q, k, v, nm=FP32):
     """Non-causal softmax attention, scale 1/sqrt(D); q,k,v [B,H,L,D] — wan_video_dit.py:60-65, F.sdpa."""
     q, k, v = nm.r(q), nm.r(k), nm.r(v)
+    if USE_TORCH_SDPA and nm is FP32:
+        return torch.nn.functional.scaled_dot_product_attention(q, k, v)
     s = (q @ k.transpose(-1, -2)) / math.sqrt(q.shape[-1])
     p = torch.softmax(s, dim=-1)
     return nm.r(p @ v)
