@@ -245,8 +245,8 @@ def run_ours(args):
     L = f * h * w
     # dominant kernel: DiT self-attention.  Under sequence parallelism with the pipelined exchange every attention runs as
     # `kv_chunks` split-KV partials over L / kv_chunks keys each.
-    chunks = model.sp.kv_chunks if (world > 1 and (L // world) >= 256 * model.sp.kv_chunks) else 1
-    dom_tag = f"attn:B1:H40:Lq{L // world}:Lk{L // chunks}:D128"
+    # (the slices may be ragged: 4095 rows per rank in 4 slices = 1024,1024,1024,1023, so match on the query side only)
+    dom_tag = f"attn:B1:H40:Lq{L // world}:Lk"
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -302,14 +302,17 @@ def run_ours(args):
     e2e_sps = args.steps / (ms_e2e / 1e3)
     burst, sustained, peak_src = peaks()
     roof = None
-    if dom_tag in prof:
-        cnt, tot = prof[dom_tag]
+    dom = {t: v for t, v in prof.items() if t.startswith(dom_tag) and t.endswith(":D128") and int(t.split(":Lk")[1].split(":")[0]) > 1024}
+    if dom:
+        cnt = sum(c for c, _ in dom.values())
+        tot = sum(ms_ for _, ms_ in dom.values())
         per = tot / cnt
-        fl = 4.0 * 40 * (L // world) * (L // chunks) * 128
-        ach = fl / (per * 1e-3) / 1e12
+        fl_total = sum(c * 4.0 * 40 * (L // world) * int(t.split(":Lk")[1].split(":")[0]) * 128 for t, (c, _) in dom.items())
+        fl = fl_total / cnt
+        ach = fl_total / (tot * 1e-3) / 1e12
         traffic = None
         tp = ROOT / "profiles" / "attn_d128_dram_bytes.json"
-        if tp.exists():
+        if tp.exists() and world == 1:                   # the ncu capture is of the full-size single-GPU launch
             try:
                 traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
             except Exception:
