@@ -150,3 +150,26 @@ def test_dpt_head_matches_reference_golden():
         assert pred.shape == g["pred"][key].shape and conf.shape == g["pred"][key + "_conf"].shape
         assert rel_err(pred, g["pred"][key]) < 1e-3, (name, rel_err(pred, g["pred"][key]))
         assert rel_err(conf, g["pred"][key + "_conf"]) < 1e-3
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours): exactly one JSON line on stdout with the contract's
+    keys, whatever libraries print (stdout is re-pointed at stderr inside bench.py)."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "cpu_baseline", "impl"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "denoise_steps_per_sec" and d["unit"] == "steps/s"
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
