@@ -197,6 +197,42 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------------
 # GPU path
 # ----------------------------------------------------------------------------------------------------------------------
+def dominant_tag(L, world):
+    """Profiling-tag prefix of the dominant kernel's launches: the DiT self-attention of this rank's L / world query rows.
+    Under sequence parallelism every attention runs as split-KV partials over slices of the keys, and the slices may be ragged
+    (4095 rows per rank in 4 slices = 1024, 1024, 1024, 1023), so the match is on the query side only."""
+    return f"attn:B1:H40:Lq{L // world}:Lk"
+
+
+def roofline_from_prof(prof, L, world, step_ms_total, sustained_peak, peak_src):
+    """The `roofline` object from the CUDA-event records {tag: (launches, total_ms)} of the timed region (pure function)."""
+    tag = dominant_tag(L, world)
+
+    def lk(t):
+        return int(t.split(":Lk")[1].split(":")[0])
+
+    # the text / CLIP cross-attentions share the prefix (same q) but have 512 / 257 keys: not the dominant kernel
+    dom = {t: v for t, v in prof.items() if t.startswith(tag) and t.endswith(":D128") and lk(t) > 1024}
+    if not dom:
+        return None
+    cnt = sum(c for c, _ in dom.values())
+    tot = sum(ms_ for _, ms_ in dom.values())
+    fl_total = sum(c * 4.0 * 40 * (L // world) * lk(t) * 128 for t, (c, _) in dom.items())
+    ach = fl_total / (tot * 1e-3) / 1e12
+    traffic = None
+    tp = ROOT / "profiles" / "attn_d128_dram_bytes.json"
+    if tp.exists() and world == 1:                       # the ncu capture is of the full-size single-GPU launch
+        try:
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    return {"kernel": "attn_fwd_kernel<128> (DiT self-attention, fwb_attn_fwd / fwb_attn_fwd_partial)", "bound": "tensor",
+            "achieved": ach, "peak": sustained_peak, "unit": "TFLOP/s", "frac": ach / sustained_peak, "traffic": traffic,
+            "launches_timed": cnt, "ms_per_launch": tot / cnt, "flop_per_launch": fl_total / cnt,
+            "peak_source": peak_src + ", sustained figure (kernel timed inside a long step)",
+            "share_of_step": tot / step_ms_total}
+
+
 def run_ours(args):
     import torch
     import fwb200
@@ -243,10 +279,7 @@ def run_ours(args):
 
     # ---- timed region: device-resident inputs --------------------------------------------------------------------------
     L = f * h * w
-    # dominant kernel: DiT self-attention.  Under sequence parallelism with the pipelined exchange every attention runs as
-    # `kv_chunks` split-KV partials over L / kv_chunks keys each.
-    # (the slices may be ragged: 4095 rows per rank in 4 slices = 1024,1024,1024,1023, so match on the query side only)
-    dom_tag = f"attn:B1:H40:Lq{L // world}:Lk"
+    dom_tag = dominant_tag(L, world)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -301,27 +334,7 @@ def run_ours(args):
     steps_per_s = args.steps / (ms / 1e3)               # strong scaling: all ranks denoise ONE sample (sequence parallel)
     e2e_sps = args.steps / (ms_e2e / 1e3)
     burst, sustained, peak_src = peaks()
-    roof = None
-    dom = {t: v for t, v in prof.items() if t.startswith(dom_tag) and t.endswith(":D128") and int(t.split(":Lk")[1].split(":")[0]) > 1024}
-    if dom:
-        cnt = sum(c for c, _ in dom.values())
-        tot = sum(ms_ for _, ms_ in dom.values())
-        per = tot / cnt
-        fl_total = sum(c * 4.0 * 40 * (L // world) * int(t.split(":Lk")[1].split(":")[0]) * 128 for t, (c, _) in dom.items())
-        fl = fl_total / cnt
-        ach = fl_total / (tot * 1e-3) / 1e12
-        traffic = None
-        tp = ROOT / "profiles" / "attn_d128_dram_bytes.json"
-        if tp.exists() and world == 1:                   # the ncu capture is of the full-size single-GPU launch
-            try:
-                traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        roof = {"kernel": "attn_fwd_kernel<128> (DiT self-attention, fwb_attn_fwd)", "bound": "tensor", "achieved": ach,
-                "peak": sustained, "unit": "TFLOP/s", "frac": ach / sustained, "traffic": traffic,
-                "launches_timed": cnt, "ms_per_launch": per, "flop_per_launch": fl,
-                "peak_source": peak_src + ", sustained figure (kernel timed inside a long step)",
-                "share_of_step": tot / ms}
+    roof = roofline_from_prof(prof, L, world, ms, sustained, peak_src)
     fwd_fl = forward_flops(f, h, w, n_pcb, n_irg)
     cpu = None
     if not args.no_cpu_baseline:

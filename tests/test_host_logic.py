@@ -173,3 +173,26 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+def test_bench_roofline_aggregation():
+    """bench.roofline_from_prof: the dominant-kernel figure from the CUDA-event records, single GPU and sequence parallel with
+    ragged K|V slices; cross-attention launches (same q, 512 / 257 keys) must not be counted."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import bench
+    L = 32760
+    prof = {"attn:B1:H40:Lq32760:Lk32760:D128": (240, 240 * 20.0), "attn:B1:H40:Lq32760:Lk512:D128": (240, 160.0),
+            "attn:B1:H12:Lq32760:Lk32865:D96": (144, 700.0)}
+    r = bench.roofline_from_prof(prof, L, 1, 12600.0, 1421.6, "measured")
+    assert r["launches_timed"] == 240 and abs(r["ms_per_launch"] - 20.0) < 1e-9
+    assert abs(r["achieved"] - 4 * 40 * L * L * 128 / 20e-3 / 1e12) < 1e-6 and abs(r["frac"] - r["achieved"] / 1421.6) < 1e-12
+    assert abs(r["share_of_step"] - 4800.0 / 12600.0) < 1e-12
+    prof8 = {"attn:B1:H40:Lq4095:Lk8192:D128": (720, 720 * 0.6), "attn:B1:H40:Lq4095:Lk8184:D128": (240, 240 * 0.6),
+             "attn:B1:H40:Lq4095:Lk257:D128": (240, 10.0)}
+    r8 = bench.roofline_from_prof(prof8, L, 8, 2200.0, 1421.6, "measured")
+    assert r8["launches_timed"] == 960 and r8["traffic"] is None
+    fl = (720 * 8192 + 240 * 8184) * 4.0 * 40 * 4095 * 128
+    assert abs(r8["achieved"] - fl / (960 * 0.6e-3) / 1e12) < 1e-6
+    assert bench.roofline_from_prof({}, L, 8, 1.0, 1421.6, "x") is None
