@@ -221,7 +221,7 @@ def roofline_from_prof(prof, L, world, step_ms_total, sustained_peak, peak_src):
     ach = fl_total / (tot * 1e-3) / 1e12
     traffic = None
     tp = ROOT / "profiles" / "attn_d128_dram_bytes.json"
-    if tp.exists() and world == 1:                       # the ncu capture is of the full-size single-GPU launch
+    if tp.exists() and world == 1 and L == 32760:        # the ncu capture is of the full-size single-GPU launch
         try:
             traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
         except Exception:
