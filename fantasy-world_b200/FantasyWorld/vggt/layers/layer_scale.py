@@ -1,16 +1,21 @@
-"""Mirror of FantasyWorld/vggt/layers/layer_scale.py.  In the fused block path gamma is folded into the proj / fc2 GEMM
-epilogue (fwb_gemm_bf16 scale1 / scale2); this forward is the standalone form."""
-from typing import Union
+"""Mirror of FantasyWorld/vggt/layers/layer_scale.py (state-dict key: `gamma`).
 
+Per-channel output scale of the VGGT residual branches.  On the fused block path gamma never runs as its own op: it is folded
+into the epilogue of the proj / fc2 GEMM (`fwb_gemm_bf16` scale1 / scale2, see fwb200/engine.py); `forward` below is the
+standalone form kept for API parity with the reference module."""
 import torch
-from torch import Tensor, nn
+from torch import nn
 
 
 class LayerScale(nn.Module):
-    def __init__(self, dim: int, init_values: Union[float, Tensor] = 1e-5, inplace: bool = False) -> None:
+    def __init__(self, dim, init_values=1e-5, inplace=False):
         super().__init__()
-        self.inplace = inplace
-        self.gamma = nn.Parameter(init_values * torch.ones(dim))
+        start = torch.full((int(dim),), 1.0)
+        self.gamma = nn.Parameter(start * init_values)       # init_values: float or a [dim] tensor
+        self.inplace = bool(inplace)
 
-    def forward(self, x: Tensor) -> Tensor:
-        return x.mul_(self.gamma) if self.inplace else x * self.gamma
+    def forward(self, x):
+        if self.inplace:
+            x *= self.gamma
+            return x
+        return torch.mul(x, self.gamma)
