@@ -288,6 +288,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld_wait();
       TRACE(warp, j, 2);
 
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      uint32_t pk[64];
+      bool spec_done = false;
+      if (EMU == 2 && j > 0 && j != j_ragged) {
+        // EXPERIMENTAL (fwb_attn_set_tuning(2), off by default, not yet measured on hardware): speculative single pass.  The
+        // exponentials start right behind the tcgen05.ld with the running max of the previous tiles while the tile's own max
+        // is formed in the free issue slots; in the rare case that it exceeds the rescale threshold the tile is redone on the
+        // classic path below from a fresh copy of S (still intact in TMEM), so the results are bit-identical to EMU == 0.
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 128; c += 4) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(v[c]), sl2, -m_used));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), sl2, -m_used));
+          const float p2 = fast_exp2(fmaf(__uint_as_float(v[c + 2]), sl2, -m_used));
+          const float p3 = fast_exp2(fmaf(__uint_as_float(v[c + 3]), sl2, -m_used));
+          mx0 = fmaxf(mx0, __uint_as_float(v[c]));
+          mx1 = fmaxf(mx1, __uint_as_float(v[c + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(v[c + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(v[c + 3]));
+          a0 += p0; a1 += p1; a2 += p2; a3 += p3;
+          pk[c / 2] = pack_bf16x2(p0, p1);
+          pk[c / 2 + 1] = pack_bf16x2(p2, p3);
+        }
+        const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
+        if (!__any_sync(0xffffffffu, m_blk > m_used + 8.0f)) {
+          spec_done = true;
+        } else {
+          tmem_ld32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          tmem_ld32(s_tmem + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
+          tmem_ld32(s_tmem + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
+          tmem_ld_wait();
+          a0 = a1 = a2 = a3 = 0.f;
+        }
+      }
+      if (!spec_done) {
       if (j == j_ragged) {
         const int valid = p.Lk - (kv0 + j) * BKV;
         if (valid < BKV) {
@@ -331,8 +367,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         asm volatile("bar.sync %1, 64;\n\tld.volatile.shared.f32 %0, [%2];" : "=f"(z) : "r"(bar_mine), "r"(pp_addr) : "memory");
         m_used += z;
       }
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      uint32_t pk[64];
 #pragma unroll
       for (int c = 0; c < 128; c += 4) {
         const float x0 = fmaf(__uint_as_float(v[c]), sl2, -m_used);
@@ -342,11 +376,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float p0 = fast_exp2(x0);
         const float p1 = fast_exp2(x1);
         const float p2 = fast_exp2(x2);
-        const float p3 = (EMU >= 1) ? exp2_poly(x3) : fast_exp2(x3);
+        const float p3 = (EMU == 1) ? exp2_poly(x3) : fast_exp2(x3);
         a0 += p0; a1 += p1; a2 += p2; a3 += p3;
         pk[c / 2] = pack_bf16x2(p0, p1);
         pk[c / 2 + 1] = pack_bf16x2(p2, p3);
       }
+      }  // !spec_done
       const float blk_sum = (a0 + a1) + (a2 + a3);
       if (pingpong)
         asm volatile("st.volatile.shared.f32 [%0], %1;\n\tbar.arrive %2, 64;" ::"r"(pp_addr + 4 + 4 * threadIdx.x), "f"(blk_sum),
@@ -885,6 +920,7 @@ int launch_attn_emu(int emu, const CUtensorMap& tq, const CUtensorMap& tk, const
                     int H, cudaStream_t stream) {
   switch (emu) {
     case 0: return launch_attn<D, 0>(tq, tk, tv, p, B, H, stream);
+    case 2: return launch_attn<D, 2>(tq, tk, tv, p, B, H, stream);
     default: return launch_attn<D, 1>(tq, tk, tv, p, B, H, stream);
   }
 }
