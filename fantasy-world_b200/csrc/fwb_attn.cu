@@ -291,7 +291,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       uint32_t pk[64];
       bool spec_done = false;
-      if (EMU == 2 && j > 0 && j != j_ragged) {
+      if (EMU == 2 && !pingpong && j > 0 && j != j_ragged) {   // (not combined with the ping-pong switch)
         // EXPERIMENTAL (fwb_attn_set_tuning(2), off by default, not yet measured on hardware): speculative single pass.  The
         // exponentials start right behind the tcgen05.ld with the running max of the previous tiles while the tile's own max
         // is formed in the free issue slots; in the rare case that it exceeds the rescale threshold the tile is redone on the
