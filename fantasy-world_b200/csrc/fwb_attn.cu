@@ -120,6 +120,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __shared__ uint64_t q_full[2], k_full[ST], k_empty[ST], v_full[ST], v_empty[ST], s_full[2], p_full[2], o_full[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float pp_scratch[1 + 256];   // MUFU ping-pong pins (see attn2_kernel)
+  __shared__ uint64_t p_half[2];          // EMU == 3 only: first 64 keys of P_i written
 
   const uint32_t warp = warp_id_uniform();
   const uint32_t lane = lane_id();
@@ -152,6 +153,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);  // one arrive per softmax warp
       mbar_init(&o_full[i], 1);
+      if constexpr (EMU == 3) mbar_init(&p_half[i], 4);
     }
     for (int s = 0; s < ST; ++s) {
       mbar_init(&k_full[s], 1);
@@ -238,11 +240,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t vs = j % ST, vph = (j / ST) & 1;
         for (int i = 0; i < 2; ++i) {
           TRACE1(8, j, i * 3 + 0);
+          if constexpr (EMU == 3) {
+            // EXPERIMENTAL (fwb_attn_set_tuning(3), not yet measured): P handed over in two 64-key halves, so the first four
+            // PV K-steps run on the tensor pipe under the second half of the tile's exponentials
+            auto issue_pv_half = [&](int half, bool acc) {
+              const uint32_t va = v_addr + vs * Cfg::kTileBytes;
+              const uint32_t d_tmem = tmem_base + Cfg::kColO + i * D;
+              const uint32_t a_tmem = tmem_base + Cfg::kColS + i * 128;
+#pragma unroll
+              for (int kk = 0; kk < BKV / 32; ++kk) {
+                const int k2 = half * (BKV / 32) + kk;
+                umma_ts(d_tmem, a_tmem + k2 * 8, make_smem_desc(va + k2 * 2048, 16384, 1024, SWZ_128B), idesc_pv, acc || kk > 0);
+              }
+            };
+            mbar_wait(&p_half[i], j & 1);
+            if (i == 0) mbar_wait(&v_full[vs], vph);
+            tc_fence_after();
+            issue_pv_half(0, j > 0);
+            mbar_wait(&p_full[i], j & 1);
+            TRACE1(8, j, i * 3 + 1);
+            tc_fence_after();
+            issue_pv_half(1, true);
+          } else {
           mbar_wait(&p_full[i], j & 1);
           TRACE1(8, j, i * 3 + 1);
           if (i == 0) mbar_wait(&v_full[vs], vph);
           tc_fence_after();
           issue_pv(i, vs, j > 0);
+          }
           if (i == 1) tc_commit(&v_empty[vs]);
           if (j + 1 < n_kv) {
             const uint32_t ks = (j + 1) % ST, kph = ((j + 1) / ST) & 1;
@@ -380,6 +405,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         a0 += p0; a1 += p1; a2 += p2; a3 += p3;
         pk[c / 2] = pack_bf16x2(p0, p1);
         pk[c / 2 + 1] = pack_bf16x2(p2, p3);
+        if constexpr (EMU == 3) {
+          if (c == 60) {   // P of keys 0..63 is complete: hand it to the MMA warp now
+            tmem_st32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_half[i]);
+          }
+        }
       }
       }  // !spec_done
       const float blk_sum = (a0 + a1) + (a2 + a3);
@@ -389,7 +423,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                      : "memory");
       l_sum += blk_sum;
       TRACE(warp, j, 4);
-      tmem_st32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+      if constexpr (EMU != 3) tmem_st32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
       tmem_st32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
       tmem_st_wait();
       tc_fence_before();
@@ -921,6 +955,7 @@ int launch_attn_emu(int emu, const CUtensorMap& tq, const CUtensorMap& tk, const
   switch (emu) {
     case 0: return launch_attn<D, 0>(tq, tk, tv, p, B, H, stream);
     case 2: return launch_attn<D, 2>(tq, tk, tv, p, B, H, stream);
+    case 3: return launch_attn<D, 3>(tq, tk, tv, p, B, H, stream);
     default: return launch_attn<D, 1>(tq, tk, tv, p, B, H, stream);
   }
 }

@@ -108,8 +108,8 @@ int fwb_attn_merge(const float* part, const float* lse, const fwb_tensor4_t* out
                    fwb_stream_t stream);
 
 /* Tuning hook: how many of every 4 softmax elements use the FMA-pipe exp2 polynomial instead of MUFU.EX2
- * (-1 = built-in default per head_dim, 0 = MUFU only, 1 = polynomial for 1 of 4, 2 = EXPERIMENTAL speculative single-pass softmax
- * of the v1 kernel (bit-identical results by construction, not yet measured); 100 / 101 = tail split off / on; 200 / 201 / 202 = kernel
+ * (-1 = built-in default per head_dim, 0 = MUFU only, 1 = polynomial for 1 of 4, 2 / 3 = EXPERIMENTAL variants of the v1 kernel
+ * (speculative single-pass softmax / P handed over in two halves; bit-identical results by construction, not yet measured); 100 / 101 = tail split off / on; 200 / 201 / 202 = kernel
  * variant default / v1 / decoupled attn2; 1000 / 1001 = attn2 MUFU ping-pong off / on).  Changes results only below bf16 resolution of P. */
 int fwb_attn_set_tuning(int exp2_poly_quarters);
 

@@ -230,11 +230,13 @@ def test_attention_kernel_variants(fwb, variant, B, H, Lq, Lk, D):
 
 
 @pytest.mark.skipif(__import__("os").environ.get("FWB_EXPERIMENTAL") != "1", reason="experimental kernel option, FWB_EXPERIMENTAL=1 to run")
+@pytest.mark.parametrize("code", [2, 3])
 @pytest.mark.parametrize("B,H,Lq,Lk,D", [(1, 3, 1000, 3000, 128), (1, 12, 1560, 1565, 96), (2, 4, 300, 1300, 64)])
-def test_attention_speculative_softmax_is_bit_identical(fwb, B, H, Lq, Lk, D):
+def test_attention_experimental_variants_are_bit_identical(fwb, code, B, H, Lq, Lk, D):
     """fwb_attn_set_tuning(2): exponentials of a KV tile start with the running max of the previous tiles and the tile is redone
-    only if its own max exceeds the rescale threshold — same arithmetic on every path, so the output must equal the default's
-    bit for bit (keys scaled up along the sequence so that the redo path is exercised too)."""
+    only if its own max exceeds the rescale threshold; (3): P handed to the MMA warp in two 64-key halves.  Same arithmetic in
+    the same order on every path, so the output must equal the default's bit for bit (keys scaled up along the sequence so that
+    the redo / rescale paths are exercised too)."""
     torch.manual_seed(5)
     q = _bf(torch.randn(B, Lq, H, D, device="cuda") * 2)
     k = _bf(torch.randn(B, Lk, H, D, device="cuda") * torch.linspace(0.2, 3, Lk, device="cuda").view(1, Lk, 1, 1))
@@ -242,7 +244,7 @@ def test_attention_speculative_softmax_is_bit_identical(fwb, B, H, Lq, Lk, D):
     try:
         fwb.lib.fwb_attn_set_tuning(201)
         ref = fwb.attention(q, k, v)
-        fwb.lib.fwb_attn_set_tuning(2)
+        fwb.lib.fwb_attn_set_tuning(code)
         out = fwb.attention(q, k, v)
         torch.cuda.synchronize()
     finally:
