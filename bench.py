@@ -27,9 +27,12 @@ import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
-for p in (ROOT, ROOT / "fantasy-world_b200"):
-    if str(p) not in sys.path:
-        sys.path.insert(0, str(p))
+PKG = ROOT / "fantasy-world_b200"
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+# NOTE: fantasy-world_b200/ (the kernel-backed `FantasyWorld` mirror + fwb200) is put on sys.path by run_ours() only.  The
+# reference arm (--impl reference) imports the UNMODIFIED reference, whose package is also called `FantasyWorld`, and must
+# neither see the mirror nor map libfwb200.so.
 
 STEP_FLOP_C2 = 4.267e15          # algorithmic FLOP per denoise step at C2 (SURVEY Appendix C / BASELINE.md §2)
 
@@ -116,79 +119,161 @@ def usable_cores():
     return n
 
 
-_CPU_SD = None
-
-
-def cpu_sample(f=1, h=30, w=52, text_len=512, reps=1):
-    """One PCB DiT block + one VGGT frame block + one IRG block at f,h,w (full 14B widths), fp32, all host threads.
-    Returns (seconds, algorithmic FLOPs, description)."""
-    import torch
-    from fwb200.synth import synth_tensor
-    from oracle import fw_oracle as O
-    torch.set_num_threads(usable_cores())
-    schema = json.loads((ROOT / "tests" / "golden" / "schema_reduced.json").read_text())
-    keys = [k for k in schema if k.startswith(("pipe.dit.blocks.0.", "vggt.aggregator.frame_blocks.0.", "IRGBlock.0.",
-                                                "vggt.aggregator.camera_token", "vggt.aggregator.register_token"))]
-    global _CPU_SD
-    if _CPU_SD is None:                                  # weights are generated once per process
-        _CPU_SD = {k: synth_tensor(k, schema[k], 0, "cpu") for k in keys}
-    sd = _CPU_SD
-    g = torch.Generator().manual_seed(1024)
-    L, P = f * h * w, 5 + h * w
-    x = torch.randn(1, L, 5120, generator=g)
-    tok = torch.randn(f, P, 1024, generator=g)
-    ctx = torch.randn(1, 257 + text_len, 5120, generator=g)
-    t_mod = torch.randn(1, 6, 5120, generator=g) * 0.1
-    e0 = torch.randn(1, 6, 1024, generator=g) * 0.1
-    plucker = torch.randn(1, L, 2048, generator=g)
-    tab, tab_d, tab_a = O.rope_table_3d(128, f, h, w), O.rope_table_3d(96, f, h, w), O.rope_table_3d_with_extra(96, f, h, w, 5)
-    _, pos = O.aggregator_input(sd, "vggt.aggregator", torch.zeros(1, f, h, w, 1024))
-    O.USE_TORCH_SDPA = True      # time what the reference runs on CPU (F.scaled_dot_product_attention), not the explicit restatement
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        for _ in range(reps):
-            x1 = O.dit_block(sd, "pipe.dit.blocks.0", x, ctx, t_mod, tab, plucker)
-            tk = O.vggt_block(sd, "vggt.aggregator.frame_blocks.0", tok, pos, e0)
-            O.irg_block(sd, "IRGBlock.0", x1, tk, ctx, t_mod, tab, tab_d, tab_a, pos, e0, plucker)
-    dt = (time.perf_counter() - t0) / reps
-    O.USE_TORCH_SDPA = False
-    # the oracle recomputes the context K/V inside every block (as the reference does): count them
+def sample_flops(f, h, w, text_len=512):
+    """Algorithmic FLOPs of the CPU sample (1 PCB DiT block + 1 VGGT frame block + 1 IRG block at f,h,w).  The reference
+    recomputes the context K/V and the camera group1 projection inside every block (no hoisting): counted."""
+    L = f * h * w
     extra_kv = 2 * 2 * (text_len + 257) * 5120 * 5120 * 2 + 2 * 2 * L * 2048 * 2048
-    flops = forward_flops(f, h, w, 1, 1, text_len) - 2 * L * 5120 * 1024 + extra_kv
-    return dt, flops, f"1 PCB DiT block + 1 VGGT frame block + 1 IRG block at f,h,w={f},{h},{w} (L={L}), fp32 oracle port"
+    return forward_flops(f, h, w, 1, 1, text_len) - 2 * L * 5120 * 1024 + extra_kv
+
+
+class CpuReference:
+    """The reference's own modules on the host cores (fp32, F.scaled_dot_product_attention, all usable threads).
+
+    kind "reference": the UNMODIFIED reference staged under oracle/_ref (or /root/reference) through oracle/ref_runner.py —
+    one PCB DiTBlock, one VGGT frame Block and one IRGBlock at full 14B widths.  kind "port": oracle/fw_oracle.py, used only
+    when no reference is staged.  Only this class and tests/ touch oracle/."""
+
+    def __init__(self):
+        import torch
+        torch.set_num_threads(usable_cores())
+        self.torch = torch
+        self.kind = "port"
+        self.model = self.ns = self.R = None
+        try:
+            from oracle import ref_runner as R          # strips the mirror from sys.path, loads fwb_synth + the shim by path
+            if R.shim.reference_available():
+                self.R = R
+                self.model, self.ns = R.build(2, 1, False, "cpu")
+                self.kind = "reference"
+        except Exception as e:                           # staged copy missing / broken: fall back to the port, say so
+            self.err = f"{type(e).__name__}: {e}"
+        if self.kind == "port":
+            self._init_port()
+
+    def _init_port(self):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("fwb_synth", PKG / "fwb_synth.py")
+        S = sys.modules.get("fwb_synth") or importlib.util.module_from_spec(spec)
+        if "fwb_synth" not in sys.modules:
+            sys.modules["fwb_synth"] = S
+            spec.loader.exec_module(S)
+        schema = json.loads((ROOT / "tests" / "golden" / "schema_reduced.json").read_text())
+        keys = [k for k in schema if k.startswith(("pipe.dit.blocks.0.", "vggt.aggregator.frame_blocks.0.", "IRGBlock.0.",
+                                                    "vggt.aggregator.camera_token", "vggt.aggregator.register_token"))]
+        self.sd = {k: S.synth_tensor(k, schema[k], 0, "cpu") for k in keys}
+        self.S = S
+
+    def sample(self, f=1, h=30, w=52, text_len=512):
+        """Seconds for one sample at f,h,w; returns (seconds, algorithmic FLOPs, description)."""
+        torch = self.torch
+        if self.kind == "reference":
+            R = self.R
+            inp = R.S.synth_block_inputs(f, h, w, text_len)
+            with R.mode_ctx(self.model, self.ns, "fp32", "cpu") as dt:
+                t0 = time.perf_counter()
+                R.run_blocks_once(self.model, self.ns, inp, f, h, w, "cpu", dt)
+                sec = time.perf_counter() - t0
+            what = "UNMODIFIED reference modules (oracle/_ref)"
+        else:
+            from oracle import fw_oracle as O
+            inp = self.S.synth_block_inputs(f, h, w, text_len)
+            tab, tab_d, tab_a = O.rope_table_3d(128, f, h, w), O.rope_table_3d(96, f, h, w), O.rope_table_3d_with_extra(96, f, h, w, 5)
+            _, pos = O.aggregator_input(self.sd, "vggt.aggregator", torch.zeros(1, f, h, w, 1024))
+            O.USE_TORCH_SDPA = True      # time what the reference runs on CPU (F.scaled_dot_product_attention)
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                x1 = O.dit_block(self.sd, "pipe.dit.blocks.0", inp["x_dit"], inp["context"], inp["t_mod"], tab, inp["plucker"])
+                tk = O.vggt_block(self.sd, "vggt.aggregator.frame_blocks.0", inp["x_agg"], pos, inp["e0"])
+                O.irg_block(self.sd, "IRGBlock.0", x1, tk, inp["context"], inp["t_mod"], tab, tab_d, tab_a, pos, inp["e0"], inp["plucker"])
+            sec = time.perf_counter() - t0
+            O.USE_TORCH_SDPA = False
+            what = "fp32 oracle port (no reference staged)"
+        return sec, sample_flops(f, h, w, text_len), (f"1 PCB DiT block + 1 VGGT frame block + 1 IRG block at f,h,w={f},{h},{w} "
+                                                       f"(L={f * h * w}), fp32, {what}")
+
+    def reduced_e2e(self, f=3, h=30, w=52, text_len=512):
+        """A COMPLETE reduced problem, not extrapolated: one denoise step (2 x joint_forward + CFG + scheduler.step) of the
+        1 PCB + 1 IRG model at f,h,w through the reference's own joint_forward."""
+        if self.kind != "reference":
+            return None
+        R, torch = self.R, self.torch
+        model = self.model
+        lens = torch.ones(f, dtype=torch.long)
+        lens[1:] = 4
+        sched = model.pipe.scheduler
+        sched.set_timesteps(50)
+        with R.mode_ctx(model, self.ns, "fp32", "cpu") as dt:
+            d = R.joint_inputs(f, h, w, text_len, "cpu", dt)
+            kw = dict(clip_feature=d["clip_feature"], y=d["y"], use_gradient_checkpointing=False, plucker_fea=d["plucker_fea"],
+                      plucker_context_lens=lens)
+            t = sched.timesteps[0].unsqueeze(0).to(dt)
+            t0 = time.perf_counter()
+            pos, _ = model.joint_forward(d["latents"], timestep=t, context=d["context_pos"], **kw)
+            neg, _ = model.joint_forward(d["latents"], timestep=t, context=d["context_neg"], **kw)
+            lat = sched.step(neg + 5.0 * (pos - neg), sched.timesteps[0], d["latents"])
+            sec = time.perf_counter() - t0
+        fl = 2 * (forward_flops(f, h, w, 1, 1, text_len))
+        return {"grid": [f, h, w], "depth": "1 PCB + 1 IRG (14B widths)", "seconds_per_step": sec, "flop_per_step": fl,
+                "achieved_tflops": fl / sec / 1e12, "finite": bool(torch.isfinite(lat).all()), "extrapolated": False}
+
+
+def pick_sample_frames(sec_f1, n_samples, budget_s):
+    """Largest sample (frames of the full 30x52 token grid) whose n_samples repetitions fit the time budget, from the measured
+    1-frame sample and the FLOP ratio.  h,w are never reduced: every sample works on full C2 frames."""
+    best = 1
+    for f in (2, 3, 4, 6, 8, 12, 21):
+        if sec_f1 * sample_flops(f, 30, 52) / sample_flops(1, 30, 52) * n_samples <= budget_s:
+            best = f
+    return best
 
 
 def run_reference(args):
-    import torch
+    """--impl reference: the reference's own CPU implementation of the path on the host cores.  Every timed "step" is one
+    bounded sample of the C2 workload (contract ④); `ms_per_step` is the measured time of a sample, `value` the implied
+    denoise-steps/s of the FULL C2 step (measured FLOP/s of the reference's algorithm / 4.27 PFLOP per step) and is labelled
+    as extrapolated.  Two non-extrapolated points are added once: the same three blocks at the FULL C2 token count, and a
+    complete reduced denoise step through joint_forward."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    t_start = time.perf_counter()
+    cpu = CpuReference()
     cores = usable_cores()
-    times, flops, desc = [], 0.0, ""
-    # every step is one bounded sample; its token count is chosen once so that warmup + steps end within ~4 minutes on this host
-    # (the metric is FLOP-rate based, so a smaller sample measures the same thing)
-    h, w = 30, 52
-    t_probe = time.perf_counter()
-    dt0, _, _ = cpu_sample(h=h, w=w)
     n = args.warmup + args.steps
-    while dt0 * n > 240.0 and h > 4:
-        h, w, dt0 = h // 2, w // 2, dt0 / 4.0
-    probe_s = time.perf_counter() - t_probe
+    sec1, _, _ = cpu.sample(f=1)
+    fs = pick_sample_frames(sec1, n, args.cpu_budget)
+    times, flops, desc = [], 0.0, ""
     for i in range(n):
-        dt, flops, desc = cpu_sample(h=h, w=w, reps=1)
+        dt, flops, desc = cpu.sample(f=fs)
         if i >= args.warmup:
             times.append(dt)
     dt = sum(times) / len(times)
-    desc += f" (probe {probe_s:.1f} s)"
     rate = flops / dt                                   # FLOP/s of the reference algorithm on this host
     steps_per_s = rate / STEP_FLOP_C2
+    extras = {}
+    spent = time.perf_counter() - t_start
+    est_full = dt * sample_flops(21, 30, 52) / flops
+    if not args.no_cpu_full and est_full < max(60.0, 420.0 - spent):
+        fdt, ffl, fdesc = cpu.sample(f=21)
+        extras["full_token_sample"] = {"sample": fdesc, "seconds": fdt, "achieved_tflops": ffl / fdt / 1e12,
+                                       "implied_steps_per_s": ffl / fdt / STEP_FLOP_C2, "extrapolated_from_blocks": True}
+    else:
+        extras["full_token_sample"] = {"skipped": "--no-cpu-full" if args.no_cpu_full else f"estimated {est_full:.0f} s exceeds the remaining budget"}
+    if not args.no_cpu_full:
+        try:
+            extras["reduced_e2e"] = cpu.reduced_e2e()
+        except Exception as e:
+            extras["reduced_e2e"] = {"error": f"{type(e).__name__}: {e}"}
     line = {"metric": "denoise_steps_per_sec", "value": steps_per_s, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 / steps_per_s, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": "Wan2.1-I2V-14B-480P shape, latents 1x16x21x60x104 (81 frames), 16 PCB + 24 IRG, CFG 2 forwards/step",
-                       "note": "each timed step is a bounded sample; steps/s = measured FLOP/s / 4.267 PFLOP per step"},
-            "cpu_baseline": {"value": steps_per_s, "unit": "steps/s", "cores": cores, "kind": "port", "sample": desc,
-                             "sample_seconds": dt, "achieved_tflops": rate / 1e12},
+                       "note": "each timed step is ONE bounded sample (ms_per_step = its measured time); value = measured FLOP/s of the "
+                               "reference's algorithm / 4.267 PFLOP per C2 step, i.e. EXTRAPOLATED to the full step",
+                       "same_config": False, "sample_frames": fs},
+            "cpu_baseline": {"value": steps_per_s, "unit": "steps/s", "cores": cores, "kind": cpu.kind, "sample": desc,
+                             "sample_seconds": dt, "achieved_tflops": rate / 1e12, **extras},
             "e2e": {"value": steps_per_s, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -233,7 +318,37 @@ def roofline_from_prof(prof, L, world, step_ms_total, sustained_peak, peak_src):
             "share_of_step": tot / step_ms_total}
 
 
+def _subprocess_json(cmd, timeout):
+    """Run a helper process and parse the last stdout line as JSON ({"error": ...} on failure — a baseline leg must never
+    take the measurement down with it)."""
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "PYTHONPATH"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        if r.returncode != 0:
+            return {"error": f"rc {r.returncode}: {r.stderr.strip()[-400:]}"}
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
+def gpu_reference_step(f, h, w, n_pcb, n_irg):
+    """The UNMODIFIED reference on this same B200: full-depth model under torch.autocast(bf16), one timed
+    denoise step through its own joint_forward + scheduler (oracle/ref_runner.py `step`, separate process), after one warm-up."""
+    if not ((ROOT / "oracle" / "_ref" / "FantasyWorld").exists() or Path("/root/reference/FantasyWorld").exists()):
+        return {"unavailable": "reference not staged (python oracle/make_ref.py)"}
+    out = _subprocess_json([sys.executable, str(ROOT / "oracle" / "ref_runner.py"), "step", "--device", "cuda", "--grid", str(f), str(h), str(w),
+                            "--pcb", str(n_pcb), "--irg", str(n_irg), "--steps", "1", "--warmup", "1", "--modes", "bf16_fa2"], timeout=900)
+    if "ms_per_step" in out:
+        out["steps_per_s"] = 1e3 / out["ms_per_step"]
+        out["what"] = "unmodified reference (oracle/_ref), model.to(bf16) + torch.autocast(cuda, bf16), same synthetic shapes, same GPU"
+    return out
+
+
 def run_ours(args):
+    if str(PKG) not in sys.path:
+        sys.path.insert(0, str(PKG))
     import torch
     import fwb200
     from fwb200.synth import build_fusion_model, synth_inputs
@@ -336,15 +451,21 @@ def run_ours(args):
     burst, sustained, peak_src = peaks()
     roof = roofline_from_prof(prof, L, world, ms, sustained, peak_src)
     fwd_fl = forward_flops(f, h, w, n_pcb, n_irg)
+    full = (f, h, w, n_pcb, n_irg) == (21, 30, 52, 16, 24)
     cpu = None
     if not args.no_cpu_baseline:
-        dt, cfl, desc = cpu_sample()
-        if dt < 6.0:                                     # fast host: take a larger sample (10-30 s of CPU work)
-            dt, cfl, desc = cpu_sample(f=min(4, int(12.0 / dt) + 1))
-        rate = cfl / dt
-        cpu = {"value": rate / (2 * fwd_fl), "unit": "steps/s", "cores": usable_cores(), "kind": "port", "sample": desc,
-               "sample_seconds": dt, "achieved_tflops": rate / 1e12}
-    full = (f, h, w, n_pcb, n_irg) == (21, 30, 52, 16, 24)
+        # the reference's CPU path, in its own process (its package is called FantasyWorld like the mirror loaded here):
+        # 2 bounded samples (1 warm-up) sized for ~20 s of CPU work
+        ref = _subprocess_json([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                                "--cpu-budget", "30", "--no-cpu-full"], timeout=900)
+        cpu = ref.get("cpu_baseline") or ref
+        if isinstance(cpu, dict):
+            cpu.pop("reduced_e2e", None), cpu.pop("full_token_sample", None)
+    gpu_ref = None
+    if world == 1 and args.gpu_reference != "off":
+        del model, inp, host, cond
+        torch.cuda.empty_cache()
+        gpu_ref = gpu_reference_step(f, h, w, n_pcb, n_irg)
     line = {"metric": "denoise_steps_per_sec", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
@@ -358,7 +479,8 @@ def run_ours(args):
                        "l2": "per-step working set (37 GB weights + >1 GB activations) exceeds the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_sps, "unit": "steps/s", "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                     "api": "FantasyWorldFusionModel.denoise_step from pinned host latents; conditioning uploaded once per run inside the timed region"},
-            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}
+            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+            "gpu_reference": gpu_ref}
     if args.breakdown:
         agg = sorted(((t, c, ms_) for t, (c, ms_) in prof.items()), key=lambda r: -r[2])
         line["breakdown_ms_per_step"] = [{"tag": t, "launches_per_step": c / args.steps, "ms_per_step": m / args.steps} for t, c, m in agg[:40]]
@@ -400,6 +522,10 @@ def main():
     ap.add_argument("--irg", type=int, default=24)
     ap.add_argument("--breakdown", action="store_true", help="time every fwb200 launch with CUDA events and add a per-kernel table")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gpu-reference", default="auto", choices=["auto", "off"],
+                    help="N=1: also time the unmodified reference (oracle/_ref) on the same GPU, in its own process")
+    ap.add_argument("--cpu-budget", type=float, default=200.0, help="--impl reference: seconds for warmup + steps samples")
+    ap.add_argument("--no-cpu-full", action="store_true", help="--impl reference: skip the extra full-token-count sample")
     args = ap.parse_args()
     protect_stdout()
     if args.impl == "reference":

@@ -23,7 +23,7 @@ def schema():
 def synth_state_dict():
     """fp32 CPU state_dict with the reference's key schema (reduced depth: 1 PCB + 1 IRG), values from the per-key
     seeded generator — identical to what tools/make_golden.py loaded into the reference."""
-    from fwb200.synth import synth_tensor
+    from fwb_synth import synth_tensor
     return {k: synth_tensor(k, shape, seed=0, device="cpu") for k, shape in schema().items()}
 
 

@@ -133,7 +133,7 @@ def test_dpt_head_matches_reference_golden():
     the oracle and compare with the reference's depth / point outputs (index chunking 4 / 16, temporal 4x, activations)."""
     import torch.nn as nn
     from FantasyWorld.vggt.heads.dpt_head import DPTHead_3D_Causal
-    from fwb200.synth import synth_inputs
+    from fwb_synth import synth_inputs
     g = gold("joint_forward.pt")
     sd = synth_state_dict()
     f, h, w = g["grid"]

@@ -44,7 +44,7 @@ def test_irg_block_config1():
 
 
 def _inputs(g):
-    from fwb200.synth import synth_inputs
+    from fwb_synth import synth_inputs
     f, h, w = g["grid"]
     return synth_inputs(f, h, w, device="cpu", seed=1024, text_len=g["text_len"], dtype=torch.float32)
 
@@ -109,7 +109,7 @@ def test_wan22_joint_forward_reduced():
     """Wan2.2-Fun-A14B-Control-Camera variant (no CLIP, control adapter): oracle vs the reference's model_wan22.joint_forward."""
     import json
     from _common import GOLD
-    from fwb200.synth import synth_inputs, synth_tensor
+    from fwb_synth import synth_inputs, synth_tensor
     g = gold("joint_forward_wan22.pt")
     schema = json.loads((GOLD / "schema_wan22_reduced.json").read_text())
     sd = {k: synth_tensor(k, shape, 0, "cpu") for k, shape in schema.items()}

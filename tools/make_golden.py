@@ -35,7 +35,7 @@ HEAD_LAYER_IDX = [0, 0, 0, 0]  # reduced depth has a single intermediate; DPT de
 
 def main():
     from ref_shim import build_reference_fusion
-    from fwb200.synth import synth_init, synth_inputs  # per-key seeded init shared with the tests
+    from fwb_synth import synth_init, synth_inputs  # per-key seeded init shared with the tests
 
     torch.manual_seed(0)
     torch.set_grad_enabled(False)

@@ -14,7 +14,7 @@ sys.path.insert(0, str(ROOT / "fantasy-world_b200"))
 from ref_shim import install_stubs
 install_stubs()
 import importlib
-from fwb200.synth import synth_init
+from fwb_synth import synth_init
 
 mod = importlib.import_module("FantasyWorld.diffsynth_wan21.models.pose_adaptor_ac3d")
 torch.manual_seed(0)

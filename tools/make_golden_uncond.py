@@ -20,7 +20,7 @@ TEXT_LEN = 64
 
 def main():
     from ref_shim import build_reference_fusion
-    from fwb200.synth import synth_init
+    from fwb_synth import synth_init
 
     torch.manual_seed(0)
     torch.set_grad_enabled(False)

@@ -36,7 +36,7 @@ dit21.FLASH_ATTN_2_AVAILABLE = False
 dit21.FLASH_ATTN_3_AVAILABLE = False
 dit21.SAGE_ATTN_AVAILABLE = False
 vggt_mod = importlib.import_module("FantasyWorld.vggt.models.vggt")
-from fwb200.synth import synth_init, synth_inputs
+from fwb_synth import synth_init, synth_inputs
 
 torch.manual_seed(0)
 torch.set_grad_enabled(False)
