@@ -369,9 +369,14 @@ def run_ours(args):
     model = build_fusion_model(num_dit_layers=n_pcb + n_irg, start_index=n_pcb, device=dev, seed=0, heads=False)
     model.pipe.device = dev
     inp = synth_inputs(f, h, w, device=dev, seed=1024, text_len=512)       # one sample, replicated inputs
+    par = "single"
     if world > 1:
-        from fwb200.sp import SPContext
-        model.sp = SPContext()                                               # tokens sharded over the ranks
+        par = args.parallel if args.parallel != "auto" else ("cfg" if world % 2 == 0 else "sp")
+        if par == "cfg":
+            model.enable_cfg_parallel()       # pos / neg forwards on the two halves of the node, each half token-sharded
+        else:
+            from fwb200.sp import SPContext
+            model.sp = SPContext()                                           # tokens sharded over all ranks
     lens = torch.ones(f, dtype=torch.long, device=dev)
     lens[1:] = 4
     sched = model.pipe.scheduler
@@ -394,7 +399,8 @@ def run_ours(args):
 
     # ---- timed region: device-resident inputs --------------------------------------------------------------------------
     L = f * h * w
-    dom_tag = dominant_tag(L, world)
+    shards = world // 2 if par == "cfg" else world          # ranks one forward's tokens are sharded over
+    dom_tag = dominant_tag(L, shards)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -449,9 +455,17 @@ def run_ours(args):
     steps_per_s = args.steps / (ms / 1e3)               # strong scaling: all ranks denoise ONE sample (sequence parallel)
     e2e_sps = args.steps / (ms_e2e / 1e3)
     burst, sustained, peak_src = peaks()
-    roof = roofline_from_prof(prof, L, world, ms, sustained, peak_src)
+    roof = roofline_from_prof(prof, L, shards, ms, sustained, peak_src)
     fwd_fl = forward_flops(f, h, w, n_pcb, n_irg)
     full = (f, h, w, n_pcb, n_irg) == (21, 30, 52, 16, 24)
+    sp_stats = (model.sp.n_gathers, model.sp.gather_bytes) if model.sp is not None else (0, 0)
+    if par == "cfg":
+        par_desc = (f"cfg2 x sp{world // 2}: conditional / unconditional forward on the two halves of the node, each half token-sharded "
+                    f"sequence parallel (1 all-gather of packed K|V per attention inside a half), 1 prediction swap per step")
+    elif par == "sp":
+        par_desc = f"sp{world} (token-sharded sequence parallel, 1 all-gather of packed K|V per attention)"
+    else:
+        par_desc = "single"
     cpu = None
     if not args.no_cpu_baseline:
         # the reference's CPU path, in its own process (its package is called FantasyWorld like the mirror loaded here):
@@ -473,9 +487,9 @@ def run_ours(args):
                        f"latents 1x16x{f}x{2 * h}x{2 * w}, {n_pcb} PCB + {n_irg} IRG blocks, 2 forwards/step (CFG 5.0), random-init",
                        "tokens_video": L, "tokens_geometry": f * (5 + h * w), "flop_per_step": 2 * fwd_fl,
                        "achieved_tflops_per_gpu": 2 * fwd_fl * args.steps / (ms / 1e3) / 1e12 / world,
-                       "parallelism": f"sp{world} (token-sharded sequence parallel, 1 all-gather of packed K|V per attention)" if world > 1 else "single",
-                       "sp_gathers_per_step": (model.sp.n_gathers / max(1, args.warmup + 2 * args.steps)) if world > 1 else 0,
-                       "sp_gather_bytes_per_step": (model.sp.gather_bytes / max(1, args.warmup + 2 * args.steps)) if world > 1 else 0,
+                       "parallelism": par_desc,
+                       "sp_gathers_per_step": sp_stats[0] / max(1, args.warmup + 2 * args.steps),
+                       "sp_gather_bytes_per_step": sp_stats[1] / max(1, args.warmup + 2 * args.steps),
                        "l2": "per-step working set (37 GB weights + >1 GB activations) exceeds the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_sps, "unit": "steps/s", "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                     "api": "FantasyWorldFusionModel.denoise_step from pinned host latents; conditioning uploaded once per run inside the timed region"},
@@ -522,6 +536,8 @@ def main():
     ap.add_argument("--irg", type=int, default=24)
     ap.add_argument("--breakdown", action="store_true", help="time every fwb200 launch with CUDA events and add a per-kernel table")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallel", default="auto", choices=["auto", "cfg", "sp"],
+                    help="N > 1: cfg = CFG-parallel x sequence-parallel halves (default for even N), sp = sequence parallel over all ranks")
     ap.add_argument("--gpu-reference", default="auto", choices=["auto", "off"],
                     help="N=1: also time the unmodified reference (oracle/_ref) on the same GPU, in its own process")
     ap.add_argument("--cpu-budget", type=float, default=200.0, help="--impl reference: seconds for warmup + steps samples")

@@ -78,7 +78,11 @@ class CrossAttentionAdapterProcessor(nn.Module):
             cache = self.__dict__["_fwb_pl"] = E.IdCache(2)
 
         def build():
-            all_zero = bool(torch.all(plucker_fea == 0).item())
+            # the reference tests the WHOLE tensor (camera_control.py:111); a sequence-parallel rank only holds its row slice, so
+            # FusionCore._local_rows stamps the slice with the flag of the full tensor (a rank whose slice happens to be all
+            # zero must still apply the shift: it is group1's bias + group2(x), not zero)
+            flag = getattr(plucker_fea, "_fwb_all_zero", None)
+            all_zero = bool(torch.all(plucker_fea == 0).item()) if flag is None else bool(flag)
             p1 = None if all_zero else E.lin(E.as_bf16(plucker_fea).reshape(-1, plucker_fea.shape[-1]), self.k_proj.group1,
                                              round_flags=ops.ROUND_AFTER_BIAS)
             return all_zero, p1

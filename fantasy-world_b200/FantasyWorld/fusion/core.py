@@ -22,6 +22,29 @@ class FusionCore(nn.Module):
     `start_index`, `cross_attention_list`, `freqs_bicross`; optional `sp` (fwb200.sp.SPContext) turns on sequence parallelism."""
 
     sp = None
+    cfgp = None     # fwb200.sp.CFGParallel: the two CFG forwards of a step on the two halves of the node (sets .sp itself)
+
+    def enable_cfg_parallel(self):
+        """Collective over the default process group: split the ranks into a conditional and an unconditional half
+        (each sequence-parallel inside) — see fwb200.sp.CFGParallel.  denoise_step then evaluates ONE forward per rank."""
+        from fwb200.sp import CFGParallel
+        self.cfgp = CFGParallel()
+        self.sp = self.cfgp.sp
+        return self.cfgp
+
+    def _cfg_forwards(self, latents, t, context_pos, context_neg, kw, return_prediction):
+        """(pred_pos, pred_neg, prediction) of one step.  Serial: both forwards here (reference order, model_wan21.py:295-317).
+        CFG-parallel: this rank evaluates only its half's forward and the halves swap predictions; the geometry-head
+        prediction exists on the conditional half only (the reference takes it from the conditional pass)."""
+        if self.cfgp is None:
+            pred_pos, pred = self.joint_forward(latents, timestep=t, context=context_pos, return_prediction=return_prediction, **kw)
+            pred_neg, _ = self.joint_forward(latents, timestep=t, context=context_neg, **kw)
+            return pred_pos, pred_neg, pred
+        role = self.cfgp.role
+        mine, pred = self.joint_forward(latents, timestep=t, context=context_pos if role == 0 else context_neg,
+                                        return_prediction=return_prediction and role == 0, **kw)
+        pred_pos, pred_neg = self.cfgp.exchange(mine)
+        return pred_pos, pred_neg, pred
 
     # ---- loop-invariant inputs (SURVEY Appendix E) ------------------------------------------------------------------------
     def embed_context(self, context, clip_feature=None):
@@ -58,7 +81,12 @@ class FusionCore(nn.Module):
         cache = self.__dict__.get("_fwb_rows")
         if cache is None:
             cache = self.__dict__["_fwb_rows"] = E.IdCache(4)
-        return cache.get((t,), (r0, r1), lambda: t[:, r0:r1].contiguous())
+        def build():
+            loc = t[:, r0:r1].contiguous()
+            loc._fwb_all_zero = bool(torch.all(t == 0).item())     # all-zero test of the FULL tensor (camera AdaLN skip, see processor)
+            return loc
+
+        return cache.get((t,), (r0, r1), build)
 
     def _control_tokens(self, control):
         """Wan2.2 control adapter output as tokens [L, dim]: a conv stack over the camera latents that depends only on the

@@ -153,11 +153,12 @@ class FantasyWorldFusionModel(FusionCore):
         t = t_host.unsqueeze(0).to(dtype=pipe.torch_dtype, device=dev)   # bf16 timestep, as the reference (:292-293)
         kw = dict(clip_feature=clip_feature, y=y, use_gradient_checkpointing=False, camera_token=camera_token,
                   plucker_fea=plucker_fea, plucker_context_lens=plucker_context_lens)
-        pred_pos, pred = self.joint_forward(latents, timestep=t, context=context_pos, return_prediction=return_prediction, **kw, **extra)
         dsigma = sched.dsigma(t_host)
         if cfg_scale != 1.0 and context_neg is not None:
-            pred_neg, _ = self.joint_forward(latents, timestep=t, context=context_neg, **kw, **extra)
+            pred_pos, pred_neg, pred = self._cfg_forwards(latents, t, context_pos, context_neg, {**kw, **extra}, return_prediction)
             ops.cfg_euler_step_(latents, pred_pos.contiguous(), pred_neg.contiguous(), cfg_scale, dsigma)
         else:
+            assert self.cfgp is None, "CFG parallelism needs cfg_scale != 1 and a negative context"
+            pred_pos, pred = self.joint_forward(latents, timestep=t, context=context_pos, return_prediction=return_prediction, **kw, **extra)
             ops.cfg_euler_step_(latents, pred_pos.contiguous(), pred_pos.contiguous(), 1.0, dsigma)
         return latents, pred

@@ -119,10 +119,10 @@ def denoise_step_experts(model_high: FantasyWorldFusionModel, model_low: Fantasy
     model = model_high if float(t_host.to(torch.bfloat16)) > timestep_boundary else model_low
     t = t_host.unsqueeze(0).to(dtype=torch.bfloat16, device=latents.device)
     kw = dict(y=y, use_gradient_checkpointing=False, camera_token=None, control_camera_latents_input=control_camera_latents_input)
-    pos, pred = model.joint_forward(latents, timestep=t, context=context_pos, return_prediction=return_prediction, **kw)
     if cfg_scale != 1.0 and context_neg is not None:
-        neg, _ = model.joint_forward(latents, timestep=t, context=context_neg, **kw)
+        pos, neg, pred = model._cfg_forwards(latents, t, context_pos, context_neg, kw, return_prediction)   # serial or CFG-parallel
         ops.cfg_euler_step_(latents, pos.contiguous(), neg.contiguous(), cfg_scale, sched.dsigma(t_host))
     else:
+        pos, pred = model.joint_forward(latents, timestep=t, context=context_pos, return_prediction=return_prediction, **kw)
         ops.cfg_euler_step_(latents, pos.contiguous(), pos.contiguous(), 1.0, sched.dsigma(t_host))
     return latents, pred

@@ -8,6 +8,13 @@ weights replicated, ONE all-gather of packed K|V per attention.
   everything else  (LayerNorm, modulation, GEMMs, RoPE, gates, text/CLIP cross-attention against the replicated context,
                    camera AdaLN with token-aligned features) is token-local
 
+CFG parallelism on top (SURVEY §8e "alternative"): a denoise step is TWO independent joint_forwards
+(conditional and unconditional context, fusion/model_wan21.py:295-317).  With an even number of ranks the two forwards run
+concurrently on the two halves of the node, each half sequence-parallel over world/2 ranks, and the halves swap their
+64-channel predictions once per step (CFGParallel.exchange: one 8 MB all-gather inside a 2-rank pair group).  Compared
+with sequence parallelism over all ranks this halves the K|V bytes every rank receives per attention, doubles the rows per
+shard (better tile-wave occupancy) and halves the number of collectives on the critical path.
+
 The reference has no live multi-GPU path (its Ulysses hooks import a module that is not in the tree, SURVEY §2.1 C1);
 this is new functionality.  Collectives go through torch.distributed (NCCL on GPUs, gloo in the CPU tests).
 """
@@ -109,7 +116,9 @@ class SPContext:
         out = []
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ready)
-            for c, n in enumerate(sizes):
+            x.record_stream(self.comm_stream)               # x and the buffers are consumed on the side stream: tell the
+            for c, n in enumerate(sizes):                    # caching allocator, or a later main-stream allocation could reuse them
+                bufs[c].record_stream(self.comm_stream)
                 dist.all_gather_into_tensor(bufs[c], x[offs[c]: offs[c] + n], group=self.group)
                 ev = torch.cuda.Event()
                 ev.record(self.comm_stream)
@@ -135,6 +144,8 @@ class SPContext:
         ev = torch.cuda.Event()
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ready)
+            xp.record_stream(self.comm_stream)               # incl. the padded temporary of a short shard (freed on return otherwise)
+            buf.record_stream(self.comm_stream)
             dist.all_gather_into_tensor(buf, xp, group=self.group)
             ev.record(self.comm_stream)
         self.n_gathers += 1
@@ -179,3 +190,38 @@ class SPContext:
         self.gather_bytes += buf.numel() * buf.element_size()
         buf = buf.view(self.world, m, *C)
         return torch.cat([buf[r, : sizes[r]] for r in range(self.world)], dim=0)
+
+
+class CFGParallel:
+    """Classifier-free-guidance parallelism: ranks [0, world/2) evaluate the conditional forward (role 0), ranks
+    [world/2, world) the unconditional one (role 1); rank r and rank r + world/2 form a pair that swaps predictions.
+
+    Built collectively (every rank of the default group must construct it at the same point: dist.new_group is collective).
+      .role   0 = conditional (context_pos), 1 = unconditional (context_neg)
+      .sp     SPContext over this half (None when the half is a single rank)
+      .exchange(pred) -> (pred_pos, pred_neg), both on every rank
+    """
+
+    def __init__(self):
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if world < 2 or world % 2:
+            raise ValueError(f"CFG parallelism needs an even number of ranks, got {world}")
+        half = world // 2
+        self.world, self.rank, self.half = world, rank, half
+        self.role = 0 if rank < half else 1
+        halves = [dist.new_group(ranks=list(range(0, half))), dist.new_group(ranks=list(range(half, world)))]
+        pairs = [dist.new_group(ranks=[r, r + half]) for r in range(half)]
+        self.pair_group = pairs[rank % half]
+        self.sp = SPContext(halves[self.role]) if half > 1 else None
+        self.n_exchanges = 0
+        self.exchange_bytes = 0
+
+    def exchange(self, pred: torch.Tensor):
+        """This rank's prediction (full tensor, identical on all ranks of its half) -> (conditional, unconditional)."""
+        pred = pred.contiguous()
+        both = torch.empty((2, *pred.shape), device=pred.device, dtype=pred.dtype)
+        # pair group rank order = (r, r + half) = (pos, neg); flat views: gloo insists on [world * n] <- [n]
+        dist.all_gather_into_tensor(both.view(-1), pred.view(-1), group=self.pair_group)
+        self.n_exchanges += 1
+        self.exchange_bytes += both.numel() * both.element_size()
+        return both[0], both[1]

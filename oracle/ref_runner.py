@@ -68,10 +68,12 @@ def build(n_layers, start_index, heads, device, seed=0):
                                                  rope_params(1024, 2 * (d // 6))], dim=1)
         model.eval()
     else:
+        # the constructors' own initialisers run on `device` (fast on the GPU); dtype=None skips the shim's CPU-generator
+        # randomisation of zero-initialised tensors — synth_init below overwrites every parameter anyway
         with torch.device(device):
             model, ns = shim.build_reference_fusion(num_dit_layers=n_layers, start_index=start_index, heads=heads, seed=seed,
-                                                    flash_attn=True)
-        model.to(device)
+                                                    flash_attn=True, dtype=None)
+        model.to(device=device, dtype=torch.float32)
     S.synth_init(model, seed)          # generator on the parameter's device: the caller does the same -> identical weights
     model.pipe.device = device
     return model, ns

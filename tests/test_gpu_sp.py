@@ -61,6 +61,20 @@ def _worker(rank, world, port, ret):
             out, _ = model.joint_forward(inp["latents"], **kw)
         rel = float((out.float() - ref.float()).norm() / ref.float().norm())
         assert rel < 1e-2, rel                              # merge re-association flips a few bf16 roundings, which then propagate
+        # CFG parallelism at 2 ranks: rank 0 = conditional forward, rank 1 = unconditional forward (no sharding inside a half),
+        # one swap of the predictions: the step must be BIT-IDENTICAL to the serial two-forward step on one GPU
+        model.sp = None
+        sched = model.pipe.scheduler
+        sched.set_timesteps(50)
+        lens = torch.ones(f, dtype=torch.long, device=dev)
+        lens[1:] = 4
+        skw = dict(clip_feature=inp["clip_feature"], y=inp["y"], plucker_fea=inp["plucker_fea"], plucker_context_lens=lens, cfg_scale=5.0)
+        lat_ref, _ = model.denoise_step(inp["latents"].clone(), 3, inp["context_pos"], inp["context_neg"], **skw)
+        cp = model.enable_cfg_parallel()
+        assert cp.role == rank and model.sp is None
+        lat_cp, _ = model.denoise_step(inp["latents"].clone(), 3, inp["context_pos"], inp["context_neg"], **skw)
+        assert torch.equal(lat_cp, lat_ref), float((lat_cp.float() - lat_ref.float()).abs().max())
+        assert cp.n_exchanges == 1
         ret[rank] = True
     finally:
         dist.destroy_process_group()

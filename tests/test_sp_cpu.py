@@ -71,3 +71,38 @@ def test_layout_at_baseline_sizes():
     assert lay.geo_range(7) == ((21 - 2) * 1565, 21 * 1565) and lay.video_range(3) == (3 * 4095, 4 * 4095)
     lay = SPLayout(4, 21, 45, 80)
     assert lay.video_rows == [18900] * 4 and lay.frames == [6, 5, 5, 5]
+
+
+def _cfg_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fwb200.sp import CFGParallel
+        cp = CFGParallel()
+        half = world // 2
+        assert cp.role == (0 if rank < half else 1) and cp.half == half
+        assert (cp.sp is None) == (half == 1)
+        if cp.sp is not None:                                # each half is its own sequence-parallel group
+            assert cp.sp.world == half and cp.sp.rank == rank % half
+            lay = cp.sp.set_grid(5, 2, 3)
+            r0, r1 = lay.video_range(cp.sp.rank)
+            rows = torch.arange(r0, r1, dtype=torch.float32)[:, None] + 1000.0 * cp.role
+            allr = cp.sp.all_gather_rows(rows.contiguous(), lay.video_rows)
+            assert torch.equal(allr[:, 0], torch.arange(lay.L, dtype=torch.float32) + 1000.0 * cp.role)   # never mixes the halves
+        # every rank of a half holds that half's prediction; the pair swap gives (conditional, unconditional) everywhere
+        mine = torch.full((1, 4, 2, 3), float(10 + cp.role))
+        pos, neg = cp.exchange(mine)
+        assert torch.equal(pos, torch.full_like(mine, 10.0)) and torch.equal(neg, torch.full_like(mine, 11.0))
+        assert cp.n_exchanges == 1 and cp.exchange_bytes == 2 * mine.numel() * 4
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_cfg_parallel_groups_and_exchange_gloo(world):
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_cfg_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world))
