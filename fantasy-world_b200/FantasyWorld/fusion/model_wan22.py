@@ -34,6 +34,10 @@ def load_lora(pipeline, lora_path, multiplier, sub_transformer_name):
     table = {name.replace(".", "_"): mod for name, mod in root.named_modules() if hasattr(mod, "weight")}
     groups = defaultdict(dict)
     for key, value in load_file(lora_path).items():
+        if ".lora_A.default." in key or ".lora_B.default." in key:
+            # reference behaviour (model_wan22.py:33-36): it strips 21 of the 22 characters of `_lora_A_default_weight`, cannot
+            # resolve the resulting layer name and skips the entry; a drop-in must leave those weights untouched too
+            continue
         k = key
         for a, b in ((".lora_A.default.", ".lora_down."), (".lora_B.default.", ".lora_up."), (".lora_A.", ".lora_down."), (".lora_B.", ".lora_up.")):
             k = k.replace(a, b)
@@ -50,14 +54,27 @@ def load_lora(pipeline, lora_path, multiplier, sub_transformer_name):
             if layer.startswith(prefix):
                 layer = layer[len(prefix):]
         groups[layer][elem] = value
+    device, dtype = getattr(pipeline, "device", "cpu"), getattr(pipeline, "torch_dtype", torch.bfloat16)
     for layer, el in groups.items():
         mod = table.get(layer)
         if mod is None or "up" not in el or "down" not in el:
             continue
-        up, down = el["up"].float(), el["down"].float()
-        alpha = (float(el["alpha"]) / up.shape[1]) if "alpha" in el else 1.0
-        delta = (up.flatten(1) @ down.flatten(1)).reshape(mod.weight.shape)
-        mod.weight.data += (multiplier * alpha * delta).to(mod.weight.device, mod.weight.dtype)
+        # arithmetic as the reference does it (model_wan22.py:100-117): factors cast to the pipeline dtype (bf16), the rank-r product
+        # in that dtype, scaled and accumulated into the weight in that dtype — so merged checkpoints are bit-identical
+        up, down = el["up"].to(device, dtype), el["down"].to(device, dtype)
+        alpha = (el["alpha"].item() / up.shape[1]) if "alpha" in el else 1.0
+        w = mod.weight.data.to(device, dtype)
+        if up.dim() == 4:
+            w += multiplier * alpha * torch.mm(up.squeeze(3).squeeze(2), down.squeeze(3).squeeze(2)).unsqueeze(2).unsqueeze(3)
+        else:
+            w += multiplier * alpha * torch.mm(up, down)
+        mod.weight.data = w.to(mod.weight.device, mod.weight.dtype)
+
+
+def select_high_noise_expert(t_host: torch.Tensor, timestep_boundary: float = 900.0, dtype=torch.bfloat16) -> bool:
+    """Expert choice of inference_wan22.py:229-240: the timestep is cast to the sampler dtype (bf16) first, then compared —
+    `t.item() > boundary` picks the high-noise expert."""
+    return float(t_host.to(dtype)) > timestep_boundary
 
 
 class FantasyWorldFusionModel(FusionCore):
@@ -116,7 +133,7 @@ def denoise_step_experts(model_high: FantasyWorldFusionModel, model_low: Fantasy
     by timestep, two forwards (CFG), fused guidance + Euler update."""
     sched = model_high.pipe.scheduler
     t_host = sched.timesteps[step]
-    model = model_high if float(t_host.to(torch.bfloat16)) > timestep_boundary else model_low
+    model = model_high if select_high_noise_expert(t_host, timestep_boundary) else model_low
     t = t_host.unsqueeze(0).to(dtype=torch.bfloat16, device=latents.device)
     kw = dict(y=y, use_gradient_checkpointing=False, camera_token=None, control_camera_latents_input=control_camera_latents_input)
     if cfg_scale != 1.0 and context_neg is not None:

@@ -140,6 +140,8 @@ def test_joint_forward_with_heads_vs_golden(model, fp32_rope_angles):
     assert rel_err(pred["depth_conf"].cpu(), g["pred"]["depth_conf"]) < 8e-2
     assert rel_err(pred["world_points_conf"].cpu(), g["pred"]["world_points_conf"]) < 8e-2
     assert rel_err(pred["pose_enc"].cpu(), g["pred"]["pose_enc"]) < 8e-2
+    assert rel_err(pred["world_points"].cpu(), g["pred"]["world_points"]) < 8e-2, rel_err(pred["world_points"].cpu(), g["pred"]["world_points"])
+    assert set(pred) == set(g["pred"])                         # every head output of the reference is produced and compared
     # second call reuses every hoisted invariant (context K/V, tables): identical result
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         out2, none = model.joint_forward(inp["latents"], timestep=ts, context=inp["context_pos"], clip_feature=inp["clip_feature"],
@@ -271,3 +273,26 @@ def test_wan22_joint_forward_vs_reference_golden(fp32_rope_angles):
     assert none is None and out.shape == g["out"].shape
     e = rel_err(out.cpu(), g["out"])
     assert e < 3e-2, e
+
+
+def test_geometry_heads_index_exact_on_cuda():
+    """SURVEY §8 a19 on the CUDA path: which tokens reach which head stage (DPT layer selection, `[:, f0:f1, 5:]` slices,
+    4-/16-frame chunking; camera token slice + 4x temporal expansion) — torch.equal against the reference's own record."""
+    from _head_index import record_head_indexing
+    from FantasyWorld.vggt.heads.camera_head import CameraHead
+    from FantasyWorld.vggt.heads.dpt_head import DPTHead_3D_Causal
+    from fwb_synth import synth_init
+    g = gold("head_index.pt")
+    wrap = torch.nn.Module()
+    wrap.vggt = torch.nn.Module()
+    wrap.vggt.depth_head = DPTHead_3D_Causal(dim_in=2048, output_dim=2, activation="exp", conf_activation="expp1", patch_size=16)
+    wrap.vggt.camera_head = CameraHead(dim_in=2048)
+    synth_init(wrap, seed=0, gen_device="cpu")
+    wrap = wrap.to("cuda").to(torch.bfloat16).eval()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        rec = record_head_indexing(wrap.vggt.depth_head, wrap.vggt.camera_head, device="cuda", dtype=torch.bfloat16)
+    gold_rec = g["records"]
+    assert [(n, tuple(s)) for n, s, _ in rec] == [(n, tuple(s)) for n, s, _ in gold_rec]
+    for (n, _, v), (_, _, gv) in zip(rec, gold_rec):
+        if gv is not None:
+            assert torch.equal(v, gv), n

@@ -205,3 +205,37 @@ def test_reduced_joint_forward_with_heads_at_c2_vs_reference_cuda_bf16(ref_joint
         print(f"[ref-parity] joint/pred/{k}: {m}")
         assert torch.isfinite(o).all(), k
         assert m["err_ratio"] <= 1.5, (k, m)
+
+
+DEEP = dict(pcb=4, irg=4, grid=(3, 8, 12))
+
+
+def test_depth_drift_4pcb_4irg_vs_reference_cuda_bf16(tmp_path_factory):
+    """Error growth over depth: 4 PCB + 4 IRG blocks (8 DiT blocks, 4 frame + 4 global VGGT blocks, 4 adapters).  After 8 blocks the
+    bf16 streams of two correct implementations have decorrelated roundings, so element-wise agreement is meaningless; what
+    must hold is protocol (ii): our distance to the fp32 golden stays within 1.5x of the reference's own bf16 distance."""
+    import fwb200
+    from fwb200.synth import build_fusion_model
+    from fwb_synth import synth_inputs
+    if not _staged():
+        pytest.skip("reference not staged")
+    d = tmp_path_factory.mktemp("ref_deep")
+    f, h, w = DEEP["grid"]
+    rep = _run_ref(["joint", "--device", "cuda", "--grid", f, h, w, "--text-len", 64, "--modes", "bf16_fa2,fp32", "--out", d,
+                    "--pcb", DEEP["pcb"], "--irg", DEEP["irg"]])
+    REPORT["reference_run_deep"] = rep
+    fwb200.require_device()
+    model = build_fusion_model(num_dit_layers=DEEP["pcb"] + DEEP["irg"], start_index=DEEP["pcb"], device="cuda", seed=0, heads=False)
+    inp = synth_inputs(f, h, w, device="cuda", seed=1024, text_len=64)
+    lens = torch.ones(f, dtype=torch.long, device="cuda")
+    lens[1:] = 4
+    ts = torch.tensor([996.0], device="cuda", dtype=torch.bfloat16)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        out, _ = model.joint_forward(inp["latents"], timestep=ts, context=inp["context_pos"], clip_feature=inp["clip_feature"], y=inp["y"],
+                                     use_gradient_checkpointing=False, plucker_fea=inp["plucker_fea"], plucker_context_lens=lens)
+    ref = torch.load(d / "joint_bf16_fa2.pt")["out"]
+    gold = torch.load(d / "joint_fp32.pt")["out"]
+    m = metrics(out.cpu(), ref, gold)
+    REPORT["deep/latent_out"] = m
+    print(f"[ref-parity] deep 4+4: {m}")
+    assert m["err_ratio"] <= 1.5, m

@@ -201,3 +201,61 @@ def test_bench_roofline_aggregation():
     fl = (720 * 8192 + 240 * 8184) * 4.0 * 40 * 4095 * 128
     assert abs(r8["achieved"] - fl / (960 * 0.6e-3) / 1e12) < 1e-6
     assert bench.roofline_from_prof({}, L, 8, 1.0, 1421.6, "x") is None
+
+
+def _compare_head_records(rec, gold_rec, only_prefix=None):
+    gold_rec = [r for r in gold_rec if only_prefix is None or r[0].startswith(only_prefix)]
+    assert [(n, tuple(s)) for n, s, _ in rec] == [(n, tuple(s)) for n, s, _ in gold_rec]
+    for (n, _, v), (_, _, gv) in zip(rec, gold_rec):
+        assert (v is None) == (gv is None), n
+        if v is not None:
+            assert torch.equal(v, gv), n          # the SAME tokens, in the same order, reach this stage
+
+
+def test_dpt_head_index_selection_and_chunking_match_reference():
+    """layer selection [23,17,11,7], the [:, f0:f1, 5:] slices of the 4-latent-frame chunks and the 16-video-frame
+    chunks of the fusion stage, recorded by hooks on integer-coded tokens, are identical to the reference's (golden written by
+    tools/make_golden_head_index.py from the unmodified reference)."""
+    from _head_index import record_head_indexing
+    from FantasyWorld.vggt.heads.dpt_head import DPTHead_3D_Causal
+    from fwb_synth import synth_init
+    g = gold("head_index.pt")
+    wrap = torch.nn.Module()
+    wrap.vggt = torch.nn.Module()
+    wrap.vggt.depth_head = DPTHead_3D_Causal(dim_in=2048, output_dim=2, activation="exp", conf_activation="expp1", patch_size=16)
+    synth_init(wrap, seed=0, gen_device="cpu")
+    rec = record_head_indexing(wrap.vggt.depth_head.eval())
+    _compare_head_records(rec, g["records"], only_prefix="dpt.")
+
+
+def test_lora_merge_and_expert_switch_match_reference(tmp_path):
+    """`load_lora` (reference: fusion/model_wan22.py:18-118) merges kohya- and PEFT-style LoRA files into the DiT
+    weights bit-identically to the unmodified reference, and the high-/low-noise expert choice over the 50-step schedule
+    (inference_wan22.py:229-240) is the reference's.  Golden: tools/make_golden_lora.py."""
+    import types
+    from safetensors.torch import save_file
+    from FantasyWorld.diffsynth_wan22.models.wan_video_dit import WanModel
+    from FantasyWorld.diffsynth_wan22.schedulers.flow_match import FlowMatchScheduler
+    from FantasyWorld.fusion.model_wan22 import load_lora, select_high_noise_expert
+    from fwb_synth import synth_init
+    g = gold("lora_merge.pt")
+    for style, sd in g["loras"].items():
+        model = WanModel(**g["cfg"])
+        wrap = torch.nn.Module()
+        wrap.dit = model
+        synth_init(wrap, seed=0, gen_device="cpu")
+        model.to(torch.bfloat16)
+        before = {k: v.clone() for k, v in model.state_dict().items()}
+        f = tmp_path / f"{style}.safetensors"
+        save_file({k: v.contiguous() for k, v in sd.items()}, str(f))
+        load_lora(types.SimpleNamespace(device="cpu", torch_dtype=torch.bfloat16, dit=model), str(f), 0.55, "dit")
+        after = model.state_dict()
+        changed = 0
+        for k, ref in g["merged"][style].items():
+            assert torch.equal(after[k], ref), (style, k)
+            changed += int(not torch.equal(after[k], before[k]))
+        assert changed == (0 if style == "peft_default" else 3), (style, changed)   # the three named layers; `.default` keys: skipped, as the reference
+    sched = FlowMatchScheduler(shift=5, sigma_min=0.0, extra_one_step=True)
+    sched.set_timesteps(50)
+    assert [select_high_noise_expert(t) for t in sched.timesteps] == g["high_noise_steps"]
+    assert 0 < sum(g["high_noise_steps"]) < 50
