@@ -16,7 +16,9 @@
 // Variants measured on B200 and NOT kept (profiles/r01_attention_variants.md): two softmax threads per row (v2, same speed:
 // the exponentials of a tile cost ~1024 clk of MUFU per SM sub-partition whatever the thread count), P handed over in
 // four 32-key chunks (v3, slower: four mbarrier wake-ups per tile on the MMA thread cost more than the overlap buys),
-// FMA-pipe exp2 polynomial for 25-75 % of the elements (slower: the softmax warps are issue/latency bound, not MUFU bound).
+// a SCALAR FMA-pipe exp2 polynomial for 25-75 % of the elements (slower: 8 issue slots per element), a speculative single-pass
+// softmax and a two-half P hand-off (round 2, profiles/r02_attn_ab_emu{2,3}.log: no gain; removed).  What IS kept from that line
+// of work is softmax_exp() below: packed f32x2 arithmetic (FFMA2 / FADD2) and a PACKED exp2 polynomial on a fraction of the pairs.
 // A second kernel (attn2, further down) decouples S and P in TMEM and is the default at head_dim 64; both share the tile schedule
 // with the key-split tail (attn_tail_merge_kernel) and the split-KV partial outputs.
 // head_dim 96 (adapter) runs on the D=128 instance: TMA zero-fills columns 96..127 and QK^T skips the dead K-steps.
@@ -79,7 +81,7 @@ __device__ __forceinline__ long long trace_clock() {
 #define TRACE1(slot, j, ev) do { } while (0)
 #endif
 
-__device__ int g_attn1_pingpong = 0;   // v1 kernel: MUFU ping-pong of the two Q tiles' exp2 phases (fwb_attn_set_tuning(1002 / 1003))
+__device__ int g_attn1_pingpong = 0;   // v1 kernel: MUFU ping-pong of the two Q tiles' exp2 phases (fwb_attn_set_mufu_pingpong(1, .))
 
 template <int D>
 struct AttnCfg {
@@ -91,22 +93,87 @@ struct AttnCfg {
   static constexpr uint32_t kColO = 256;                  // O_i at columns 256 + i*D
 };
 
-// 2^x for x in [-126, 128) on the FMA / ALU pipes (no MUFU): Cody-Waite split with round-toward-minus-infinity magic
-// add, degree-3 minimax polynomial for 2^frac (max rel. error 8.6e-5 — 45x below the bf16 rounding P receives next),
-// exponent re-inserted with an integer add.  Used for a fraction of the softmax elements because MUFU.EX2
-// (16/clk/SM) is as scarce as the tensor pipe at head_dim 128 and twice as scarce at head_dim 64.
-__device__ __forceinline__ float exp2_poly(float x) {
-  x = fmaxf(x, -126.f);
-  float r;
-  asm("add.rm.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(12582912.f));   // 1.5 * 2^23: mantissa low bits = floor(x)
-  const float f = x - (r - 12582912.f);                                 // frac in [0, 1)
-  float pz = fmaf(f, 0.07706704f, 0.22764499f);
-  pz = fmaf(pz, f, 0.69511679f);
-  pz = fmaf(pz, f, 1.0f);
-  return __int_as_float(__float_as_int(pz) + (__float_as_int(r) << 23));
+// ---- packed fp32 pairs (sm_100 FFMA2 / FADD2: one issue slot for two elements) ------------------------------------------------
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2_rm(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fsub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
 }
 
-template <int D, int EMU>
+// Exponentials of one S tile row held in registers: p[c] = 2^(v[c] * sl2 - m), packed to bf16 pairs in pk[], returns sum_c p[c]
+// (fp32, before the bf16 rounding, as flash-attn / cuDNN accumulate the row sum).
+// Budget per SM sub-partition and KV tile (two softmax warps, 256 elements): MUFU.EX2 runs at 4 lanes/clk = 8 clk per warp
+// instruction, i.e. 2048 clk for all exponentials — as much as the tile's MMA work at head_dim 128 and twice that at head_dim 64
+// (tools/ubench/mufu.cu).  So (1) the scale/subtract and the row sum are done on PAIRS (FFMA2 / FADD2: half the issue slots), and
+// (2) POLY of every 8 pairs take 2^x from the FMA / ALU pipes instead of the MUFU: Cody-Waite split with a round-toward-minus-
+// infinity magic add (FADD2.RM: mantissa low bits = floor(x)), degree-3 minimax polynomial for 2^frac on [0,1) (max rel. error
+// 8.6e-5, 45x below the bf16 rounding P receives next), exponent re-inserted with one LEA (shift-left-add) per element.
+// Cost per pair: MUFU path 1 FFMA2 + 2 MUFU + 1 FADD2 + 1 F2FP; polynomial path 2 FMNMX + 4 FFMA2 + 3 FADD2 + 2 LEA + 1 FADD2 + 1 F2FP.
+template <int N, int POLY>
+__device__ __forceinline__ float softmax_exp(const uint32_t (&v)[N], float sl2, float m, uint32_t (&pk)[N / 2]) {
+  const uint64_t S2 = pack2(sl2, sl2), M2 = pack2(-m, -m);
+  const uint64_t MAGIC = pack2(12582912.f, 12582912.f);   // 1.5 * 2^23
+  const uint64_t C3 = pack2(0.07706704f, 0.07706704f), C2 = pack2(0.22764499f, 0.22764499f), C1 = pack2(0.69511679f, 0.69511679f),
+                 C0 = pack2(1.0f, 1.0f);
+  uint64_t acc0 = pack2(0.f, 0.f), acc1 = pack2(0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < N; c += 2) {
+    const int pair = c / 2;
+    uint64_t x = ffma2(pack2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), S2, M2);
+    float p0, p1;
+    if (POLY > 0 && ((pair & 7) * POLY) % 8 < POLY) {
+      float x0, x1;
+      unpack2(x, x0, x1);
+      x = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+      const uint64_t r = fadd2_rm(x, MAGIC);
+      const uint64_t f = fsub2(x, fsub2(r, MAGIC));     // frac in [0, 1)
+      uint64_t q = ffma2(f, C3, C2);
+      q = ffma2(q, f, C1);
+      q = ffma2(q, f, C0);
+      float q0, q1, r0, r1;
+      unpack2(q, q0, q1);
+      unpack2(r, r0, r1);
+      p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(r0) << 23));
+      p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23));
+    } else {
+      float x0, x1;
+      unpack2(x, x0, x1);
+      p0 = fast_exp2(x0);
+      p1 = fast_exp2(x1);
+    }
+    if (pair & 1) acc1 = fadd2(acc1, pack2(p0, p1));
+    else acc0 = fadd2(acc0, pack2(p0, p1));
+    pk[pair] = pack_bf16x2(p0, p1);
+  }
+  float s0, s1;
+  unpack2(fadd2(acc0, acc1), s0, s1);
+  return s0 + s1;
+}
+
+template <int D, int POLY>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -120,7 +187,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __shared__ uint64_t q_full[2], k_full[ST], k_empty[ST], v_full[ST], v_empty[ST], s_full[2], p_full[2], o_full[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float pp_scratch[1 + 256];   // MUFU ping-pong pins (see attn2_kernel)
-  __shared__ uint64_t p_half[2];          // EMU == 3 only: first 64 keys of P_i written
 
   const uint32_t warp = warp_id_uniform();
   const uint32_t lane = lane_id();
@@ -153,7 +219,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);  // one arrive per softmax warp
       mbar_init(&o_full[i], 1);
-      if constexpr (EMU == 3) mbar_init(&p_half[i], 4);
     }
     for (int s = 0; s < ST; ++s) {
       mbar_init(&k_full[s], 1);
@@ -240,34 +305,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t vs = j % ST, vph = (j / ST) & 1;
         for (int i = 0; i < 2; ++i) {
           TRACE1(8, j, i * 3 + 0);
-          if constexpr (EMU == 3) {
-            // EXPERIMENTAL (fwb_attn_set_tuning(3), not yet measured): P handed over in two 64-key halves, so the first four
-            // PV K-steps run on the tensor pipe under the second half of the tile's exponentials
-            auto issue_pv_half = [&](int half, bool acc) {
-              const uint32_t va = v_addr + vs * Cfg::kTileBytes;
-              const uint32_t d_tmem = tmem_base + Cfg::kColO + i * D;
-              const uint32_t a_tmem = tmem_base + Cfg::kColS + i * 128;
-#pragma unroll
-              for (int kk = 0; kk < BKV / 32; ++kk) {
-                const int k2 = half * (BKV / 32) + kk;
-                umma_ts(d_tmem, a_tmem + k2 * 8, make_smem_desc(va + k2 * 2048, 16384, 1024, SWZ_128B), idesc_pv, acc || kk > 0);
-              }
-            };
-            mbar_wait(&p_half[i], j & 1);
-            if (i == 0) mbar_wait(&v_full[vs], vph);
-            tc_fence_after();
-            issue_pv_half(0, j > 0);
-            mbar_wait(&p_full[i], j & 1);
-            TRACE1(8, j, i * 3 + 1);
-            tc_fence_after();
-            issue_pv_half(1, true);
-          } else {
           mbar_wait(&p_full[i], j & 1);
           TRACE1(8, j, i * 3 + 1);
           if (i == 0) mbar_wait(&v_full[vs], vph);
           tc_fence_after();
           issue_pv(i, vs, j > 0);
-          }
           if (i == 1) tc_commit(&v_empty[vs]);
           if (j + 1 < n_kv) {
             const uint32_t ks = (j + 1) % ST, kph = ((j + 1) / ST) & 1;
@@ -313,42 +355,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld_wait();
       TRACE(warp, j, 2);
 
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       uint32_t pk[64];
-      bool spec_done = false;
-      if (EMU == 2 && !pingpong && j > 0 && j != j_ragged) {   // (not combined with the ping-pong switch)
-        // EXPERIMENTAL (fwb_attn_set_tuning(2), off by default, not yet measured on hardware): speculative single pass.  The
-        // exponentials start right behind the tcgen05.ld with the running max of the previous tiles while the tile's own max
-        // is formed in the free issue slots; in the rare case that it exceeds the rescale threshold the tile is redone on the
-        // classic path below from a fresh copy of S (still intact in TMEM), so the results are bit-identical to EMU == 0.
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 128; c += 4) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(v[c]), sl2, -m_used));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), sl2, -m_used));
-          const float p2 = fast_exp2(fmaf(__uint_as_float(v[c + 2]), sl2, -m_used));
-          const float p3 = fast_exp2(fmaf(__uint_as_float(v[c + 3]), sl2, -m_used));
-          mx0 = fmaxf(mx0, __uint_as_float(v[c]));
-          mx1 = fmaxf(mx1, __uint_as_float(v[c + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(v[c + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(v[c + 3]));
-          a0 += p0; a1 += p1; a2 += p2; a3 += p3;
-          pk[c / 2] = pack_bf16x2(p0, p1);
-          pk[c / 2 + 1] = pack_bf16x2(p2, p3);
-        }
-        const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
-        if (!__any_sync(0xffffffffu, m_blk > m_used + 8.0f)) {
-          spec_done = true;
-        } else {
-          tmem_ld32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          tmem_ld32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-          tmem_ld32(s_tmem + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
-          tmem_ld32(s_tmem + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
-          tmem_ld_wait();
-          a0 = a1 = a2 = a3 = 0.f;
-        }
-      }
-      if (!spec_done) {
       if (j == j_ragged) {
         const int valid = p.Lk - (kv0 + j) * BKV;
         if (valid < BKV) {
@@ -392,38 +399,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         asm volatile("bar.sync %1, 64;\n\tld.volatile.shared.f32 %0, [%2];" : "=f"(z) : "r"(bar_mine), "r"(pp_addr) : "memory");
         m_used += z;
       }
-#pragma unroll
-      for (int c = 0; c < 128; c += 4) {
-        const float x0 = fmaf(__uint_as_float(v[c]), sl2, -m_used);
-        const float x1 = fmaf(__uint_as_float(v[c + 1]), sl2, -m_used);
-        const float x2 = fmaf(__uint_as_float(v[c + 2]), sl2, -m_used);
-        const float x3 = fmaf(__uint_as_float(v[c + 3]), sl2, -m_used);
-        const float p0 = fast_exp2(x0);
-        const float p1 = fast_exp2(x1);
-        const float p2 = fast_exp2(x2);
-        const float p3 = (EMU == 1) ? exp2_poly(x3) : fast_exp2(x3);
-        a0 += p0; a1 += p1; a2 += p2; a3 += p3;
-        pk[c / 2] = pack_bf16x2(p0, p1);
-        pk[c / 2 + 1] = pack_bf16x2(p2, p3);
-        if constexpr (EMU == 3) {
-          if (c == 60) {   // P of keys 0..63 is complete: hand it to the MMA warp now
-            tmem_st32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_half[i]);
-          }
-        }
-      }
-      }  // !spec_done
-      const float blk_sum = (a0 + a1) + (a2 + a3);
+      const float blk_sum = softmax_exp<128, POLY>(v, sl2, m_used, pk);
       if (pingpong)
         asm volatile("st.volatile.shared.f32 [%0], %1;\n\tbar.arrive %2, 64;" ::"r"(pp_addr + 4 + 4 * threadIdx.x), "f"(blk_sum),
                      "r"(bar_other)
                      : "memory");
       l_sum += blk_sum;
       TRACE(warp, j, 4);
-      if constexpr (EMU != 3) tmem_st32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+      tmem_st32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
       tmem_st32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
       tmem_st_wait();
       tc_fence_before();
@@ -552,20 +535,18 @@ __global__ void attn_tail_merge_kernel(const AttnParams p, int tail) {
   }
 }
 
-template <int D, int EMU>
+template <int D, int POLY>
 int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B, int H,
                 cudaStream_t stream) {
   using Cfg = AttnCfg<D>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FWB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  static AttrOnce once;
+  if (once.need(current_device()))
+    FWB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const long long n_tiles = (long long)p.nq * H * B;
   const long long tail = n_tiles - p.n_full;
   const long long grid = p.n_full + (p.S > 1 ? tail * p.S : tail);
   FWB_CHECK(grid < (1ll << 31), "attn: grid too large");
-  attn_fwd_kernel<D, EMU><<<(unsigned)grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  attn_fwd_kernel<D, POLY><<<(unsigned)grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
   FWB_CUDA(cudaGetLastError());
   if (p.S > 1) {
     const long long total = tail * (2 * BQ) * (p.d_real / 8);
@@ -589,7 +570,7 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
 // columns), head_dim 128 -> BKV 64 (448 columns).  K/V stages are released by both MMA warps (mbarrier count 2).
 // =====================================================================================================================
 constexpr int kAttn2Threads = 352;
-__device__ int g_attn2_pingpong = 1;   // exp2 phases of the two Q tiles alternate through named barriers (fwb_attn_set_tuning(1000 / 1001))
+__device__ int g_attn2_pingpong = 1;   // exp2 phases of the two Q tiles alternate through named barriers (fwb_attn_set_mufu_pingpong(2, .))
 
 template <int D, int BK>
 struct Attn2Cfg {
@@ -606,7 +587,7 @@ struct Attn2Cfg {
   static_assert(2 * D + 2 * kTileCols <= 512, "TMEM overflow");
 };
 
-template <int D, int BK>
+template <int D, int BK, int POLY>
 __global__ void __launch_bounds__(kAttn2Threads, 1)
 attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
              const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -828,21 +809,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         m_used += z;
       }
       TRACE(warp, j, 3);
-      // (a software-pipelined variant that ties the consumers of chunk k-1 behind the MUFUs of chunk k runs at 9.7 instead of
-      // 12.3 clk per element in isolation (tools/ubench/mufu.cu) but made no difference inside the kernel; not kept)
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       uint32_t pk[BK / 2];
-#pragma unroll
-      for (int c = 0; c < BK; c += 4) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(v[c]), sl2, -m_used));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), sl2, -m_used));
-        const float p2 = fast_exp2(fmaf(__uint_as_float(v[c + 2]), sl2, -m_used));
-        const float p3 = fast_exp2(fmaf(__uint_as_float(v[c + 3]), sl2, -m_used));
-        a0 += p0; a1 += p1; a2 += p2; a3 += p3;
-        pk[c / 2] = pack_bf16x2(p0, p1);
-        pk[c / 2 + 1] = pack_bf16x2(p2, p3);
-      }
-      const float blk_sum = (a0 + a1) + (a2 + a3);
+      const float blk_sum = softmax_exp<BK, POLY>(v, sl2, m_used, pk);
       if (pingpong)
         asm volatile("st.volatile.shared.f32 [%0], %1;\n\tbar.arrive %2, 64;" ::"r"(pp_addr + 4 + 4 * threadIdx.x), "f"(blk_sum),
                      "r"(bar_other)
@@ -926,20 +894,18 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
-template <int D, int BK>
+template <int D, int BK, int POLY>
 int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B, int H,
                  cudaStream_t stream) {
   using Cfg = Attn2Cfg<D, BK>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FWB_CUDA(cudaFuncSetAttribute(attn2_kernel<D, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  static AttrOnce once;
+  if (once.need(current_device()))
+    FWB_CUDA(cudaFuncSetAttribute(attn2_kernel<D, BK, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const long long n_tiles = (long long)p.nq * H * B;
   const long long tail = n_tiles - p.n_full;
   const long long grid = p.n_full + (p.S > 1 ? tail * p.S : tail);
   FWB_CHECK(grid < (1ll << 31), "attn: grid too large");
-  attn2_kernel<D, BK><<<(unsigned)grid, kAttn2Threads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  attn2_kernel<D, BK, POLY><<<(unsigned)grid, kAttn2Threads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
   FWB_CUDA(cudaGetLastError());
   if (p.S > 1) {
     const long long total = tail * (2 * BQ) * (p.d_real / 8);
@@ -949,14 +915,25 @@ int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap
   return FWB_OK;
 }
 
+// POLY (pairs out of every 8 that take 2^x from the FMA-pipe polynomial) is a template parameter: dispatch over the built values
 template <int D>
-int launch_attn_emu(int emu, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
-                    int H, cudaStream_t stream) {
-  switch (emu) {
-    case 0: return launch_attn<D, 0>(tq, tk, tv, p, B, H, stream);
+int launch_attn_poly(int poly, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
+                     int H, cudaStream_t stream) {
+  switch (poly) {
     case 2: return launch_attn<D, 2>(tq, tk, tv, p, B, H, stream);
     case 3: return launch_attn<D, 3>(tq, tk, tv, p, B, H, stream);
-    default: return launch_attn<D, 1>(tq, tk, tv, p, B, H, stream);
+    case 4: return launch_attn<D, 4>(tq, tk, tv, p, B, H, stream);
+    default: return launch_attn<D, 0>(tq, tk, tv, p, B, H, stream);
+  }
+}
+template <int D, int BK>
+int launch_attn2_poly(int poly, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
+                      int H, cudaStream_t stream) {
+  switch (poly) {
+    case 2: return launch_attn2<D, BK, 2>(tq, tk, tv, p, B, H, stream);
+    case 3: return launch_attn2<D, BK, 3>(tq, tk, tv, p, B, H, stream);
+    case 4: return launch_attn2<D, BK, 4>(tq, tk, tv, p, B, H, stream);
+    default: return launch_attn2<D, BK, 0>(tq, tk, tv, p, B, H, stream);
   }
 }
 
@@ -993,11 +970,14 @@ __global__ void attn_merge_kernel(const float* __restrict__ part, const float* _
   *reinterpret_cast<uint4*>(out + b * o_sb + l * o_sl + h * o_sh + pc * 8) = o;
 }
 
-int g_attn_variant = 0;     // 0: per head_dim default (64 -> attn2, 96 / 128 -> v1: measured), 1: v1 kernel, 2: decoupled attn2
-                            // kernel.  fwb_attn_set_tuning(200 / 201 / 202) selects.
-int g_attn_tail_split = 1;  // fwb_attn_set_tuning(100 / 101) turns the tail split off / on (A/B measurements)
-int g_attn_emu = -1;  // -1: default (0: measured fastest on B200, the softmax is issue-bound not MUFU-bound); 0..3: number of
-                      // softmax elements out of every 4 that use exp2_poly
+// Process-wide tuning state behind the named setters of include/fwb200.h (A/B measurements, tests).  One process drives one GPU
+// (DESIGN.md), so this is not per-stream state.
+int g_attn_variant = 0;     // 0: per head_dim default (64 -> decoupled attn2, 96 / 128 -> v1: measured), 1: v1, 2: decoupled attn2
+int g_attn_tail_split = 1;  // key-split tail of the tile schedule on / off
+int g_attn_poly = -1;       // -1: per head_dim default, else 0 / 2 / 3 / 4 = pairs out of 8 on the exp2 polynomial
+
+// exp2 polynomial share per head_dim (pairs of 8); set from the A/B measurements in profiles/r02_attention.md
+inline int default_poly(int D) { return D == 64 ? 0 : 0; }
 
 // Tile schedule planner (pure host arithmetic).  n_tiles tiles on W SMs (one CTA per SM): the first floor(n/W)*W tiles run
 // unsplit; each of the `tail` remaining tiles may be split S ways along the keys -> tail * S short CTAs running in
@@ -1047,25 +1027,32 @@ extern "C" int fwb_attn_trace_read(long long* host_out, int cta) {
 }
 #endif
 
-extern "C" int fwb_attn_set_tuning(int exp2_poly_quarters) {
-  if (exp2_poly_quarters >= 1000 && exp2_poly_quarters < 100000) {
-    const int clk = (exp2_poly_quarters - 1000) & 1;
-    if (exp2_poly_quarters - 1000 >= 2) {
-      FWB_CUDA(cudaMemcpyToSymbol(g_attn1_pingpong, &clk, sizeof(int)));
-    } else {
-      FWB_CUDA(cudaMemcpyToSymbol(g_attn2_pingpong, &clk, sizeof(int)));
-    }
-    return FWB_OK;
+extern "C" int fwb_attn_set_variant(int variant) {
+  FWB_CHECK(variant >= 0 && variant <= 2, "attn_set_variant: 0 (default per head_dim), 1 (v1) or 2 (decoupled)");
+  g_attn_variant = variant;
+  return FWB_OK;
+}
+
+extern "C" int fwb_attn_set_tail_split(int enabled) {
+  g_attn_tail_split = enabled ? 1 : 0;
+  return FWB_OK;
+}
+
+extern "C" int fwb_attn_set_exp2_poly(int pairs_of_8) {
+  FWB_CHECK(pairs_of_8 == -1 || pairs_of_8 == 0 || (pairs_of_8 >= 2 && pairs_of_8 <= 4),
+            "attn_set_exp2_poly: -1 (default), 0, 2, 3 or 4 pairs out of every 8");
+  g_attn_poly = pairs_of_8;
+  return FWB_OK;
+}
+
+extern "C" int fwb_attn_set_mufu_pingpong(int kernel, int enabled) {
+  FWB_CHECK(kernel == 1 || kernel == 2, "attn_set_mufu_pingpong: kernel 1 (v1) or 2 (decoupled)");
+  const int on = enabled ? 1 : 0;
+  if (kernel == 1) {
+    FWB_CUDA(cudaMemcpyToSymbol(g_attn1_pingpong, &on, sizeof(int)));
+  } else {
+    FWB_CUDA(cudaMemcpyToSymbol(g_attn2_pingpong, &on, sizeof(int)));
   }
-  if (exp2_poly_quarters >= 200 && exp2_poly_quarters <= 202) {
-    g_attn_variant = exp2_poly_quarters - 200;
-    return FWB_OK;
-  }
-  if (exp2_poly_quarters == 100 || exp2_poly_quarters == 101) {
-    g_attn_tail_split = exp2_poly_quarters - 100;
-    return FWB_OK;
-  }
-  g_attn_emu = exp2_poly_quarters;
   return FWB_OK;
 }
 
@@ -1155,10 +1142,11 @@ static int attn_impl(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_t
       p.ws_lse = p.ws_out + (size_t)(n_tiles - n_full) * S * 2 * BQ * D;
     }
   }
+  const int poly = g_attn_poly >= 0 ? g_attn_poly : default_poly(D);
   if (variant == 2) {
-    if (D == 64) return launch_attn2<64, 128>(tq, tk, tv, p, B, H, stream);
-    return launch_attn2<128, 64>(tq, tk, tv, p, B, H, stream);
+    if (D == 64) return launch_attn2_poly<64, 128>(poly, tq, tk, tv, p, B, H, stream);
+    return launch_attn2_poly<128, 64>(poly, tq, tk, tv, p, B, H, stream);
   }
-  if (D == 64) return launch_attn_emu<64>(g_attn_emu >= 0 ? g_attn_emu : 0, tq, tk, tv, p, B, H, stream);
-  return launch_attn_emu<128>(g_attn_emu >= 0 ? g_attn_emu : 0, tq, tk, tv, p, B, H, stream);
+  if (D == 64) return launch_attn_poly<64>(poly, tq, tk, tv, p, B, H, stream);
+  return launch_attn_poly<128>(poly, tq, tk, tv, p, B, H, stream);
 }

@@ -472,11 +472,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 template <int BN, int ACT>
 int launch1(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static AttrOnce once;
+  if (once.need(current_device()))
     FWB_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = num_sms();
   if (grid > tiles) grid = tiles;
@@ -487,11 +485,9 @@ int launch1(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
 
 template <int ACT>
 int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static AttrOnce once;
+  if (once.need(current_device()))
     FWB_CUDA(cudaFuncSetAttribute(gemm2_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
-    attr_set = true;
-  }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   int pairs = num_sms() / 2;
   if (pairs > tiles) pairs = tiles;

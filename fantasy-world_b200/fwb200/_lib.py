@@ -50,7 +50,10 @@ def _load():
     vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
     lib.fwb_gemm_bf16.argtypes = [vp, i64, vp, i64, i32, i32, i32, C.POINTER(Epilogue), vp]
     lib.fwb_gemm_set_mode.argtypes = [i32]
-    lib.fwb_attn_set_tuning.argtypes = [i32]
+    lib.fwb_attn_set_variant.argtypes = [i32]
+    lib.fwb_attn_set_tail_split.argtypes = [i32]
+    lib.fwb_attn_set_exp2_poly.argtypes = [i32]
+    lib.fwb_attn_set_mufu_pingpong.argtypes = [i32, i32]
     lib.fwb_attn_fwd.argtypes = [C.POINTER(Tensor4)] * 4 + [i32, i32, i32, i32, i32, f32, i32, vp, C.c_size_t, vp]
     lib.fwb_attn_fwd_partial.argtypes = [C.POINTER(Tensor4)] * 3 + [vp, vp, i32, i32, i32, i32, i32, f32, vp, C.c_size_t, vp]
     lib.fwb_attn_merge.argtypes = [vp, vp, C.POINTER(Tensor4), i32, i32, i32, i32, i32, vp]

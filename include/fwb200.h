@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define FWB_ABI_VERSION 2
+#define FWB_ABI_VERSION 3
 
 typedef struct CUstream_st* fwb_stream_t; /* == cudaStream_t */
 
@@ -107,11 +107,18 @@ int fwb_attn_fwd_partial(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const f
 int fwb_attn_merge(const float* part, const float* lse, const fwb_tensor4_t* out, int S, int B, int H, int L, int D,
                    fwb_stream_t stream);
 
-/* Tuning hook: how many of every 4 softmax elements use the FMA-pipe exp2 polynomial instead of MUFU.EX2
- * (-1 = built-in default per head_dim, 0 = MUFU only, 1 = polynomial for 1 of 4, 2 / 3 = EXPERIMENTAL variants of the v1 kernel
- * (speculative single-pass softmax / P handed over in two halves; bit-identical results by construction, not yet measured); 100 / 101 = tail split off / on; 200 / 201 / 202 = kernel
- * variant default / v1 / decoupled attn2; 1000 / 1001 = attn2 MUFU ping-pong off / on).  Changes results only below bf16 resolution of P. */
-int fwb_attn_set_tuning(int exp2_poly_quarters);
+/* Tuning / test hooks (process-wide; one process drives one GPU).  None of them changes what is computed beyond fp32
+ * re-association or the sub-bf16 error of the exp2 polynomial; they select between measured kernel variants.
+ *   fwb_attn_set_variant        0 = default per head_dim (64 -> decoupled S/P kernel, 96 / 128 -> aliased S/P kernel), 1 / 2 = force
+ *   fwb_attn_set_tail_split     key-split tail of the tile schedule on (1, default) / off (0)
+ *   fwb_attn_set_exp2_poly      pairs out of every 8 softmax element pairs whose 2^x comes from the packed FMA-pipe polynomial
+ *                               instead of MUFU.EX2: -1 = default per head_dim, 0, 2, 3, 4 (max rel. error 8.6e-5 before P is
+ *                               rounded to bf16)
+ *   fwb_attn_set_mufu_pingpong  kernel 1 (aliased) / 2 (decoupled): alternate the exp2 phases of the two Q tiles of a CTA */
+int fwb_attn_set_variant(int variant);
+int fwb_attn_set_tail_split(int enabled);
+int fwb_attn_set_exp2_poly(int pairs_of_8);
+int fwb_attn_set_mufu_pingpong(int kernel, int enabled);
 
 /* ---- K7: LayerNorm (+affine) (+modulate) -> bf16 ------------------------------------------------------------------
  * out[r,:] = bf16( (LN(x[r,:]) * w + b) * mul + add ), any of (w,b), mul, add may be NULL.  fp32 statistics.

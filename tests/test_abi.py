@@ -17,7 +17,7 @@ def test_library_loads_and_exports_all_declared_symbols():
     lib = ctypes.CDLL(str(fwb200.library_path()))
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/fwb200.h but not exported"
-    assert fwb200.lib.fwb_abi_version() == 2
+    assert fwb200.lib.fwb_abi_version() == 3
 
 
 def test_header_has_no_torch_types():

@@ -142,7 +142,7 @@ def ours_blocks():
 # stated floors on the rtol=1e-3 / atol=1e-4 pass fraction (measured values are in profiles/r02_ref_parity.json; floors sit a few
 # points below them).  bf16 outputs: an element passes only if it rounds to the SAME bf16 value as the reference's (1 ulp = 3.9e-3
 # relative > rtol), so the fraction is the share of bit-equal elements; fp32 outputs (geometry stream) are compared at fp32 grain.
-FLOORS = {"pcb": 0.60, "frame": 0.60, "irg_x": 0.55, "irg_tokens": 0.40}
+FLOORS = {"pcb": 0.55, "frame": 0.30, "irg_x": 0.45, "irg_tokens": 0.30}
 
 
 @pytest.mark.parametrize("name", ["pcb", "frame", "irg_x", "irg_tokens"])

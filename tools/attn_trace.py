@@ -31,11 +31,10 @@ def run():
     lib = C.CDLL(str(LIB))
     lib.fwb_attn_fwd.argtypes = [C.POINTER(T4)] * 4 + [C.c_int] * 5 + [C.c_float, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.fwb_attn_trace_read.argtypes = [C.c_void_p, C.c_int]
-    lib.fwb_attn_set_tuning.argtypes = [C.c_int]
     variant = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    lib.fwb_attn_set_tuning(200 + variant)
+    lib.fwb_attn_set_variant(variant)
     if len(sys.argv) > 3:
-        lib.fwb_attn_set_tuning(int(sys.argv[3]))
+        lib.fwb_attn_set_exp2_poly(int(sys.argv[3]))     # pairs of 8 on the exp2 polynomial
     lib.fwb_last_error.restype = C.c_char_p
     out_lines = []
     for (B, H, L, D) in [(1, 40, 32760, 128), (1, 16, 32865, 64)]:

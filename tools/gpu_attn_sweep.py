@@ -1,0 +1,68 @@
+"""Interleaved timing of the attention kernel variants at the hot-path shapes (run under gpurun):
+
+    python tools/gpu_attn_sweep.py [--quick]
+
+For every shape: kernel variant (1 = S/P aliased, 2 = decoupled) x exp2-polynomial share (0, 2, 3, 4 pairs of 8) [x MUFU ping-pong
+for the aliased kernel], 3 interleaved rounds each (the box runs power-capped: +-4 % between rounds), plus cuDNN / flash SDPA of
+torch on the same tensors.  Writes gpurun_out/r02_attn_sweep.log (TFLOP/s = 4 B H Lq Lk D / time)."""
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "fantasy-world_b200"))
+import torch
+import fwb200
+
+QUICK = "--quick" in sys.argv
+
+
+def timeit(fn, iters=4, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+SHAPES = [(1, 40, 32760, 32760, 128, "DiT self"), (1, 12, 32760, 32865, 96, "adapter v<-g"), (1, 16, 32865, 32865, 64, "VGGT global"),
+          (21, 16, 1565, 1565, 64, "VGGT frame"), (1, 40, 32760, 512, 128, "cross text"), (1, 40, 8190, 32760, 128, "DiT self, 4-rank shard")]
+if QUICK:
+    SHAPES = SHAPES[:3]
+log = open(ROOT / "gpurun_out" / "r02_attn_sweep.log", "w")
+
+
+def emit(line):
+    print(line, flush=True)
+    log.write(line + "\n")
+    log.flush()
+
+
+lib = fwb200.lib
+for (B, H, Lq, Lk, D, name) in SHAPES:
+    q, k, v = (torch.randn(B, L, H, D, device="cuda").to(torch.bfloat16) for L in (Lq, Lk, Lk))
+    o = torch.empty_like(q)
+    fl = 4.0 * B * H * Lq * Lk * D
+    configs = [(var, poly, pp) for var in (1, 2) for poly in (0, 2, 3, 4) for pp in ((0, 1) if var == 1 else (1,))]
+    res = {c: [] for c in configs}
+    for rnd in range(3):
+        for c in configs:
+            var, poly, pp = c
+            lib.fwb_attn_set_variant(var)
+            lib.fwb_attn_set_exp2_poly(poly)
+            lib.fwb_attn_set_mufu_pingpong(var, pp)
+            res[c].append(fl / timeit(lambda: fwb200.attention(q, k, v, out=o)) / 1e9)
+    lib.fwb_attn_set_variant(0)
+    lib.fwb_attn_set_exp2_poly(-1)
+    lib.fwb_attn_set_mufu_pingpong(1, 0)
+    lib.fwb_attn_set_mufu_pingpong(2, 1)
+    qt, kt, vt = (t.transpose(1, 2) for t in (q, k, v))
+    sd = [fl / timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt)) / 1e9 for _ in range(3)]
+    emit(f"== {name}: B{B} H{H} Lq{Lq} Lk{Lk} D{D}   torch SDPA: " + "/".join(f"{x:.0f}" for x in sd) + " TF")
+    for c in sorted(configs, key=lambda c: -sorted(res[c])[1]):
+        emit(f"   variant {c[0]} poly {c[1]}/8 pingpong {c[2]}: " + "/".join(f"{x:.0f}" for x in res[c]) + f" TF  (median {sorted(res[c])[1]:.0f})")
+log.close()

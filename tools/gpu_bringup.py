@@ -133,11 +133,11 @@ def _time_case(kind):
             out = torch.empty_like(q)
             fl = 4 * B * H * L * L * D
             res = []
-            for emu in (0, 1):
-                fwb200.lib.fwb_attn_set_tuning(emu)
+            for poly in (0, 2, 3, 4):
+                fwb200.lib.fwb_attn_set_exp2_poly(poly)
                 ms = timeit(lambda: fwb200.attention(q, k, v, out=out), iters=3, warm=1)
-                res.append(f"emu{emu} {ms:.3f} ms {fl/ms/1e9:.0f} TF")
-            fwb200.lib.fwb_attn_set_tuning(-1)
+                res.append(f"poly{poly}/8 {ms:.3f} ms {fl/ms/1e9:.0f} TF")
+            fwb200.lib.fwb_attn_set_exp2_poly(-1)
             print("   variants: " + " | ".join(res))
             ms = timeit(lambda: fwb200.attention(q, k, v, out=out), iters=3, warm=1)
             qt, kt, vt = (t.transpose(1, 2) for t in (q, k, v))
