@@ -37,15 +37,17 @@ if str(ROOT) not in sys.path:
 STEP_FLOP_C2 = 4.267e15          # algorithmic FLOP per denoise step at C2 (SURVEY Appendix C / BASELINE.md §2)
 
 
-def forward_flops(f, h, w, n_pcb, n_irg, text_len=512):
-    """Algorithmic FLOPs of one joint_forward (attention 4*H*Lq*Lk*D, GEMM 2*M*N*K), same accounting as SURVEY App. C."""
+def forward_flops(f, h, w, n_pcb, n_irg, text_len=512, clip=True, camera_adaln=True):
+    """Algorithmic FLOPs of one joint_forward (attention 4*H*Lq*Lk*D, GEMM 2*M*N*K), same accounting as SURVEY App. C.
+    Wan2.2: clip=False (512 text tokens only), camera_adaln=False (the camera enters through the hoisted control adapter)."""
     L, P = f * h * w, 5 + h * w
     N = f * P
     C, Fd = 5120, 13824
+    ctx = text_len + (257 if clip else 0)
     dit = 2 * L * C * C * 4 + 4 * 40 * L * L * 128                        # qkvo + self-attn
-    dit += 2 * L * C * C * 2 + 4 * 40 * L * (text_len + 257) * 128         # cross q,o + attn (K/V of the context are hoisted)
+    dit += 2 * L * C * C * 2 + 4 * 40 * L * ctx * 128                      # cross q,o + attn (K/V of the context are hoisted)
     dit += 2 * L * C * Fd * 2                                              # FFN
-    cam = 2 * L * (C * 1024 + 1024 * 2048 + 2048 * 409 + 409 * C)          # camera AdaLN MLPs (group1 hoisted)
+    cam = 2 * L * (C * 1024 + 1024 * 2048 + 2048 * 409 + 409 * C) if camera_adaln else 0   # camera AdaLN MLPs (group1 hoisted)
     vg_lin = 2 * N * 1024 * (3072 + 1024 + 4096 + 4096)
     frame = vg_lin + 4 * 16 * f * P * P * 64
     glob = vg_lin + 4 * 16 * N * N * 64
@@ -53,6 +55,15 @@ def forward_flops(f, h, w, n_pcb, n_irg, text_len=512):
     total = n_pcb * (dit + cam) + n_irg * (frame + dit + glob + adapter) + min(n_irg, 9) * cam
     total += 2 * L * C * 1024                                              # projection head
     return float(total)
+
+
+def vggt_forward_flops(f, h, w, n_blocks=24):
+    """Aggregator of the stand-alone geometry branch: projection + n_blocks x (frame block + global block).  The heads'
+    convolutions are not counted (they run on cuDNN, once per video)."""
+    L, P = f * h * w, 5 + h * w
+    N = f * P
+    vg_lin = 2 * N * 1024 * (3072 + 1024 + 4096 + 4096)
+    return float(2 * L * 5120 * 1024 + n_blocks * (2 * vg_lin + 4 * 16 * f * P * P * 64 + 4 * 16 * N * N * 64))
 
 
 class ClockSampler(threading.Thread):
@@ -282,37 +293,40 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------------
 # GPU path
 # ----------------------------------------------------------------------------------------------------------------------
-def dominant_tag(L, world):
-    """Profiling-tag prefix of the dominant kernel's launches: the DiT self-attention of this rank's L / world query rows.
+def dominant_tag(L, world, H=40):
+    """Profiling-tag prefix of the dominant kernel's launches: the self-attention (H heads) of this rank's L / world query rows.
     Under sequence parallelism every attention runs as split-KV partials over slices of the keys, and the slices may be ragged
     (4095 rows per rank in 4 slices = 1024, 1024, 1024, 1023), so the match is on the query side only."""
-    return f"attn:B1:H40:Lq{L // world}:Lk"
+    return f"attn:B1:H{H}:Lq{L // world}:Lk"
 
 
-def roofline_from_prof(prof, L, world, step_ms_total, sustained_peak, peak_src):
+def roofline_from_prof(prof, L, world, step_ms_total, sustained_peak, peak_src, H=40, D=128, kernel=None):
     """The `roofline` object from the CUDA-event records {tag: (launches, total_ms)} of the timed region (pure function)."""
-    tag = dominant_tag(L, world)
+    tag = dominant_tag(L, world, H)
 
     def lk(t):
         return int(t.split(":Lk")[1].split(":")[0])
 
     # the text / CLIP cross-attentions share the prefix (same q) but have 512 / 257 keys: not the dominant kernel
-    dom = {t: v for t, v in prof.items() if t.startswith(tag) and t.endswith(":D128") and lk(t) > 1024}
+    dom = {t: v for t, v in prof.items() if t.startswith(tag) and t.endswith(f":D{D}") and lk(t) > 1024}
     if not dom:
         return None
     cnt = sum(c for c, _ in dom.values())
     tot = sum(ms_ for _, ms_ in dom.values())
-    fl_total = sum(c * 4.0 * 40 * (L // world) * lk(t) * 128 for t, (c, _) in dom.items())
+    fl_total = sum(c * 4.0 * H * (L // world) * lk(t) * D for t, (c, _) in dom.items())
     ach = fl_total / (tot * 1e-3) / 1e12
-    traffic = None
+    traffic, traffic_src = None, None
     tp = ROOT / "profiles" / "attn_d128_dram_bytes.json"
-    if tp.exists() and world == 1 and L == 32760:        # the ncu capture is of the full-size single-GPU launch
+    if tp.exists() and world == 1 and L == 32760 and D == 128:        # the ncu capture is of the full-size single-GPU launch
         try:
-            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+            rec = json.loads(tp.read_text())
+            traffic = rec.get("dram_bytes_per_launch")
+            traffic_src = rec.get("source", "ncu --set full capture, see profiles/")
         except Exception:
             traffic = None
-    return {"kernel": "attn_fwd_kernel<128> (DiT self-attention, fwb_attn_fwd / fwb_attn_fwd_partial)", "bound": "tensor",
+    return {"kernel": kernel or "attn_fwd_kernel<128> (DiT self-attention, fwb_attn_fwd / fwb_attn_fwd_partial)", "bound": "tensor",
             "achieved": ach, "peak": sustained_peak, "unit": "TFLOP/s", "frac": ach / sustained_peak, "traffic": traffic,
+            "traffic_source": traffic_src,
             "launches_timed": cnt, "ms_per_launch": tot / cnt, "flop_per_launch": fl_total / cnt,
             "peak_source": peak_src + ", sustained figure (kernel timed inside a long step)",
             "share_of_step": tot / step_ms_total}
@@ -366,9 +380,23 @@ def run_ours(args):
 
     f, h, w = args.frames, args.h, args.w
     n_pcb, n_irg = args.pcb, args.irg
-    model = build_fusion_model(num_dit_layers=n_pcb + n_irg, start_index=n_pcb, device=dev, seed=0, heads=False)
+    wan22 = args.workload == "wan22_720p"
+    model_low = None
+    if wan22:
+        # BASELINE configs[3]: Wan2.2-Fun-A14B-Control-Camera, two experts resident (high-noise / low-noise), switched by timestep
+        from fwb200.synth import build_fusion_model_wan22
+        from FantasyWorld.fusion.model_wan22 import denoise_step_experts
+        model = build_fusion_model_wan22(num_dit_layers=n_pcb + n_irg, start_index=n_pcb, device=dev, seed=0)
+        model_low = build_fusion_model_wan22(num_dit_layers=n_pcb + n_irg, start_index=n_pcb, device=dev, seed=1)
+        model_low.pipe.device = dev
+    else:
+        model = build_fusion_model(num_dit_layers=n_pcb + n_irg, start_index=n_pcb, device=dev, seed=0, heads=False)
     model.pipe.device = dev
     inp = synth_inputs(f, h, w, device=dev, seed=1024, text_len=512)       # one sample, replicated inputs
+    if wan22:
+        g = torch.Generator(device="cpu").manual_seed(77)
+        inp["control"] = torch.randn(1, 24, f, 16 * h, 16 * w, generator=g, dtype=torch.bfloat16).to(dev)   # Pluecker rays folded 4:1 in time
+        inp.pop("clip_feature"), inp.pop("plucker_fea")
     par = "single"
     if world > 1:
         par = args.parallel if args.parallel != "auto" else ("cfg" if world % 2 == 0 else "sp")
@@ -377,15 +405,27 @@ def run_ours(args):
         else:
             from fwb200.sp import SPContext
             model.sp = SPContext()                                           # tokens sharded over all ranks
+    if model_low is not None:
+        model_low.sp, model_low.cfgp = model.sp, model.cfgp                  # one set of process groups for both experts
     lens = torch.ones(f, dtype=torch.long, device=dev)
     lens[1:] = 4
     sched = model.pipe.scheduler
     sched.set_timesteps(50)
     n_sched = len(sched.timesteps)
 
+    def step_api(lat, i, c):
+        """One denoise step through the public API on conditioning dict `c`; `lat` may be a pinned host tensor."""
+        if wan22:
+            # steps 0, 17, 34, 1, ... of the 50-step schedule: both experts are exercised inside any timed window (18 of 50 steps
+            # lie above the t = 900 boundary)
+            lat_dev = lat if lat.is_cuda else lat.to(dev, non_blocking=True)
+            return denoise_step_experts(model, model_low, lat_dev.contiguous(), (i * 17) % n_sched, c["context_pos"], c["context_neg"],
+                                        c["y"], c["control"], cfg_scale=5.0)[0]
+        return model.denoise_step(lat, i % n_sched, c["context_pos"], c["context_neg"], clip_feature=c["clip_feature"],
+                                  y=c["y"], plucker_fea=c["plucker_fea"], plucker_context_lens=lens, cfg_scale=5.0)[0]
+
     def one_step(lat, i):
-        return model.denoise_step(lat, i % n_sched, inp["context_pos"], inp["context_neg"], clip_feature=inp["clip_feature"],
-                                  y=inp["y"], plucker_fea=inp["plucker_fea"], plucker_context_lens=lens, cfg_scale=5.0)[0]
+        return step_api(lat, i, inp)
 
     def barrier():
         if dist is not None:
@@ -430,13 +470,11 @@ def run_ours(args):
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    cond = {k: host[k].to(dev, non_blocking=True) for k in ("context_pos", "context_neg", "clip_feature", "y", "plucker_fea")}
+    cond = {k: host[k].to(dev, non_blocking=True) for k in host if k != "latents"}
     h2d = sum(host[k].numel() * host[k].element_size() for k in cond)
     d2h = 0
     for i in range(args.steps):
-        cur = model.denoise_step(lat_host, (args.warmup + i) % n_sched, cond["context_pos"], cond["context_neg"],
-                                 clip_feature=cond["clip_feature"], y=cond["y"], plucker_fea=cond["plucker_fea"],
-                                 plucker_context_lens=lens, cfg_scale=5.0)[0]
+        cur = step_api(lat_host, args.warmup + i, cond)
         out_host.copy_(cur, non_blocking=True)
         torch.cuda.current_stream().synchronize()       # the host needs the step's result before it can feed the next step
         lat_host.copy_(out_host)
@@ -456,8 +494,8 @@ def run_ours(args):
     e2e_sps = args.steps / (ms_e2e / 1e3)
     burst, sustained, peak_src = peaks()
     roof = roofline_from_prof(prof, L, shards, ms, sustained, peak_src)
-    fwd_fl = forward_flops(f, h, w, n_pcb, n_irg)
-    full = (f, h, w, n_pcb, n_irg) == (21, 30, 52, 16, 24)
+    fwd_fl = forward_flops(f, h, w, n_pcb, n_irg, clip=not wan22, camera_adaln=not wan22)
+    full = (f, h, w, n_pcb, n_irg) == ((21, 45, 80, 16, 24) if wan22 else (21, 30, 52, 16, 24))
     sp_stats = (model.sp.n_gathers, model.sp.gather_bytes) if model.sp is not None else (0, 0)
     if par == "cfg":
         par_desc = (f"cfg2 x sp{world // 2}: conditional / unconditional forward on the two halves of the node, each half token-sharded "
@@ -476,15 +514,17 @@ def run_ours(args):
         if isinstance(cpu, dict):
             cpu.pop("reduced_e2e", None), cpu.pop("full_token_sample", None)
     gpu_ref = None
-    if world == 1 and args.gpu_reference != "off":
+    if world == 1 and args.gpu_reference != "off" and not wan22:
         del model, inp, host, cond
         torch.cuda.empty_cache()
         gpu_ref = gpu_reference_step(f, h, w, n_pcb, n_irg)
     line = {"metric": "denoise_steps_per_sec", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": ("Wan2.1-I2V-14B-480P shape (BASELINE configs[1]): " if full else "REDUCED (not the headline config): ") +
-                       f"latents 1x16x{f}x{2 * h}x{2 * w}, {n_pcb} PCB + {n_irg} IRG blocks, 2 forwards/step (CFG 5.0), random-init",
+            "config": {"workload": ((("Wan2.2-Fun-A14B-Control-Camera 720p shape (BASELINE configs[3]), two experts resident, switched at t=900: "
+                                      if wan22 else "Wan2.1-I2V-14B-480P shape (BASELINE configs[1]): ") if full
+                                     else "REDUCED (not the headline config): ") +
+                                    f"latents 1x16x{f}x{2 * h}x{2 * w}, {n_pcb} PCB + {n_irg} IRG blocks, 2 forwards/step (CFG 5.0), random-init"),
                        "tokens_video": L, "tokens_geometry": f * (5 + h * w), "flop_per_step": 2 * fwd_fl,
                        "achieved_tflops_per_gpu": 2 * fwd_fl * args.steps / (ms / 1e3) / 1e12 / world,
                        "parallelism": par_desc,
@@ -492,12 +532,90 @@ def run_ours(args):
                        "sp_gather_bytes_per_step": sp_stats[1] / max(1, args.warmup + 2 * args.steps),
                        "l2": "per-step working set (37 GB weights + >1 GB activations) exceeds the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_sps, "unit": "steps/s", "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
-                    "api": "FantasyWorldFusionModel.denoise_step from pinned host latents; conditioning uploaded once per run inside the timed region"},
+                    "api": ("denoise_step_experts" if wan22 else "FantasyWorldFusionModel.denoise_step") +
+                           " from pinned host latents; conditioning uploaded once per run inside the timed region"},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
             "gpu_reference": gpu_ref}
     if args.breakdown:
         agg = sorted(((t, c, ms_) for t, (c, ms_) in prof.items()), key=lambda r: -r[2])
         line["breakdown_ms_per_step"] = [{"tag": t, "launches_per_step": c / args.steps, "ms_per_step": m / args.steps} for t, c, m in agg[:40]]
+    emit(line)
+
+
+def run_vggt_only(args):
+    """--workload vggt_only (BASELINE configs[4]): the stand-alone geometry branch — VGGT.forward(patch_token[1,5120,21,30,52], t) =
+    5120->1024 projection, 24 x (frame block + global block) without the adapter, camera / depth / point heads for 81 frames at
+    480x832 (reference: vggt/models/vggt.py:45-117).  One "step" = one such forward.  Single GPU (the path is once per video)."""
+    if str(PKG) not in sys.path:
+        sys.path.insert(0, str(PKG))
+    import torch
+    import fwb200
+    from fwb200.synth import build_vggt
+    assert int(os.environ.get("WORLD_SIZE", "1")) == 1, "vggt_only is a single-GPU workload"
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    fwb200.require_device()
+    f, h, w = args.frames, args.h, args.w
+    vggt = build_vggt(device=dev, seed=0, heads=True)
+    g = torch.Generator(device="cpu").manual_seed(1024)
+    patch_host = torch.randn(1, 5120, f, h, w, generator=g, dtype=torch.float32).to(torch.bfloat16).pin_memory()
+    patch = patch_host.to(dev)
+    t = torch.tensor([500.0], device=dev)
+
+    def step(p_in):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            return vggt(p_in, t=t)
+
+    for _ in range(args.warmup):
+        pred = step(patch)
+    torch.cuda.synchronize()
+    L, N = f * h * w, f * (5 + h * w)
+    sampler = ClockSampler(0)
+    sampler.start()
+    fwb200.reset_launch_count()
+    tag = dominant_tag(N, 1, H=16)
+    fwb200.prof_enable(prefixes=[tag] if not args.breakdown else None)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        pred = step(patch)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = fwb200.launch_count()
+    prof = fwb200.prof_disable()
+    ms = e0.elapsed_time(e1)
+    sampler.stop_flag.set()
+    # e2e: patch tokens from pinned host memory, every head output read back
+    outs = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in pred.items()}
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        pred = step(patch_host.to(dev, non_blocking=True))
+        for k, v in pred.items():
+            outs[k].copy_(v, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    t1.record()
+    torch.cuda.synchronize()
+    ms_e2e = t0.elapsed_time(t1)
+    burst, sustained, peak_src = peaks()
+    roof = roofline_from_prof(prof, N, 1, ms, sustained, peak_src, H=16, D=64,
+                              kernel="attn2_kernel<64,128> (VGGT global attention, H16 D64, fwb_attn_fwd)")
+    fl = vggt_forward_flops(f, h, w)
+    line = {"metric": "geometry_forwards_per_sec", "value": args.steps / (ms / 1e3), "unit": "forwards/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"VGGT geometry branch only (BASELINE configs[4]): patch tokens 1x5120x{f}x{h}x{w}, 24 frame + 24 global blocks, "
+                                   f"camera / depth / point heads for {4 * (f - 1) + 1} frames at {16 * h}x{16 * w}, random-init",
+                       "tokens_geometry": N, "flop_per_step_aggregator": fl, "achieved_tflops_aggregator": fl * args.steps / (ms / 1e3) / 1e12,
+                       "outputs": {k: list(v.shape) for k, v in pred.items()},
+                       "l2": "activations (135 MB fp32 tokens, 0.4 GB qkv) and 2.4 GB of weights exceed the 126 MB L2; no flush needed"},
+            "e2e": {"value": args.steps / (ms_e2e / 1e3), "unit": "forwards/s", "h2d_bytes_per_step": patch_host.numel() * 2,
+                    "d2h_bytes_per_step": sum(v.numel() * v.element_size() for v in outs.values()),
+                    "api": "VGGT.forward(patch_token, t) from a pinned host tensor; all head outputs copied back"},
+            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": None}
+    if args.breakdown:
+        agg = sorted(((tg, c, m_) for tg, (c, m_) in prof.items()), key=lambda r: -r[2])
+        line["breakdown_ms_per_step"] = [{"tag": tg, "launches_per_step": c / args.steps, "ms_per_step": m / args.steps} for tg, c, m in agg[:30]]
     emit(line)
 
 
@@ -529,9 +647,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="wan21_480p", choices=["wan21_480p", "wan22_720p", "vggt_only"],
+                    help="wan21_480p = BASELINE configs[1] (the headline metric); wan22_720p = configs[3] (meant for 8 GPUs); "
+                         "vggt_only = configs[4], the stand-alone geometry branch with heads")
     ap.add_argument("--frames", type=int, default=21)
-    ap.add_argument("--h", type=int, default=30)
-    ap.add_argument("--w", type=int, default=52)
+    ap.add_argument("--h", type=int, default=None)
+    ap.add_argument("--w", type=int, default=None)
     ap.add_argument("--pcb", type=int, default=16)
     ap.add_argument("--irg", type=int, default=24)
     ap.add_argument("--breakdown", action="store_true", help="time every fwb200 launch with CUDA events and add a per-kernel table")
@@ -543,7 +664,12 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=200.0, help="--impl reference: seconds for warmup + steps samples")
     ap.add_argument("--no-cpu-full", action="store_true", help="--impl reference: skip the extra full-token-count sample")
     args = ap.parse_args()
+    if args.h is None:
+        args.h, args.w = (45, 80) if args.workload == "wan22_720p" else (30, 52)
     protect_stdout()
+    if args.workload == "vggt_only" and args.impl != "reference":
+        run_vggt_only(args)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:
