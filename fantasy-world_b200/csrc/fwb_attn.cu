@@ -977,7 +977,7 @@ int g_attn_tail_split = 1;  // key-split tail of the tile schedule on / off
 int g_attn_poly = -1;       // -1: per head_dim default, else 0 / 2 / 3 / 4 = pairs out of 8 on the exp2 polynomial
 
 // exp2 polynomial share per head_dim (pairs of 8); set from the A/B measurements in profiles/r02_attention.md
-inline int default_poly(int D) { return D == 64 ? 0 : 0; }
+inline int default_poly(int D) { (void)D; return 2; }   // 2 of 8 pairs: +1 % (head_dim 128), +13 % (96), +10 % (64), r02_attn_sweep.log
 
 // Tile schedule planner (pure host arithmetic).  n_tiles tiles on W SMs (one CTA per SM): the first floor(n/W)*W tiles run
 // unsplit; each of the `tail` remaining tiles may be split S ways along the keys -> tail * S short CTAs running in

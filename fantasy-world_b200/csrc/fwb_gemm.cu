@@ -84,6 +84,55 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 #pragma unroll
   for (int c = 0; c < 32; ++c) y[c] = __uint_as_float(v[c]);
   if (colbase + 32 <= p.N) {
+    // Residual prefetch, in the coalesced (post-transpose) thread mapping used by the stores below: the loads are issued before
+    // any math, so their HBM latency overlaps the column math and the transposition instead of sitting, once per row group,
+    // between the transposition and every store (the short-K shapes — K <= 1152, fp32 geometry stream — were bound by exactly
+    // that chain: ~8000 clk of epilogue per 256x256 tile against 8192 clk of MMA).
+    float rres[32];
+    if (p.resid) {
+      if (p.out_f32) {
+        const int piece = lane & 7;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int grow = row0 + it * 4 + (lane >> 3);
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (grow < p.M) {
+            const int col = colbase + piece * 4;
+            if (p.resid_f32) {
+              b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.resid) + (size_t)grow * p.resid_ld + col);
+            } else {
+              const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + (size_t)grow * p.resid_ld + col);
+              b = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                              __uint_as_float(u.y & 0xFFFF0000u));
+            }
+          }
+          rres[4 * it] = b.x; rres[4 * it + 1] = b.y; rres[4 * it + 2] = b.z; rres[4 * it + 3] = b.w;
+        }
+      } else {
+        const int piece = lane & 3;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int grow = row0 + it * 8 + (lane >> 2);
+          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+          if (grow < p.M) {
+            const int col = colbase + piece * 8;
+            if (p.resid_f32) {
+              const float* rp = reinterpret_cast<const float*>(p.resid) + (size_t)grow * p.resid_ld + col;
+              b0 = *reinterpret_cast<const float4*>(rp);
+              b1 = *reinterpret_cast<const float4*>(rp + 4);
+            } else {
+              const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + (size_t)grow * p.resid_ld + col);
+              b0 = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                               __uint_as_float(u.y & 0xFFFF0000u));
+              b1 = make_float4(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xFFFF0000u), __uint_as_float(u.w << 16),
+                               __uint_as_float(u.w & 0xFFFF0000u));
+            }
+          }
+          rres[8 * it] = b0.x; rres[8 * it + 1] = b0.y; rres[8 * it + 2] = b0.z; rres[8 * it + 3] = b0.w;
+          rres[8 * it + 4] = b1.x; rres[8 * it + 5] = b1.y; rres[8 * it + 6] = b1.z; rres[8 * it + 7] = b1.w;
+        }
+      }
+    }
     if (p.bias) {
 #pragma unroll
       for (int c = 0; c < 32; c += 4) {
@@ -148,14 +197,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
         if (grow < p.M) {
           const int col = colbase + piece * 4;
           if (p.resid) {
-            if (p.resid_f32) {
-              const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.resid) + (size_t)grow * p.resid_ld + col);
-              t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
-            } else {
-              const uint2 b = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + (size_t)grow * p.resid_ld + col);
-              t.x += __uint_as_float(b.x << 16); t.y += __uint_as_float(b.x & 0xFFFF0000u);
-              t.z += __uint_as_float(b.y << 16); t.w += __uint_as_float(b.y & 0xFFFF0000u);
-            }
+            t.x += rres[4 * it]; t.y += rres[4 * it + 1]; t.z += rres[4 * it + 2]; t.w += rres[4 * it + 3];
           }
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)grow * p.out_ld + col) = t;
         }
@@ -172,18 +214,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
         if (grow < p.M) {
           const int col = colbase + piece * 8;
           if (p.resid) {
-            if (p.resid_f32) {
-              const float* rp = reinterpret_cast<const float*>(p.resid) + (size_t)grow * p.resid_ld + col;
-              const float4 r0 = *reinterpret_cast<const float4*>(rp), r1 = *reinterpret_cast<const float4*>(rp + 4);
-              a.x += r0.x; a.y += r0.y; a.z += r0.z; a.w += r0.w;
-              b4.x += r1.x; b4.y += r1.y; b4.z += r1.z; b4.w += r1.w;
-            } else {
-              const uint4 rb = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + (size_t)grow * p.resid_ld + col);
-              a.x += __uint_as_float(rb.x << 16); a.y += __uint_as_float(rb.x & 0xFFFF0000u);
-              a.z += __uint_as_float(rb.y << 16); a.w += __uint_as_float(rb.y & 0xFFFF0000u);
-              b4.x += __uint_as_float(rb.z << 16); b4.y += __uint_as_float(rb.z & 0xFFFF0000u);
-              b4.z += __uint_as_float(rb.w << 16); b4.w += __uint_as_float(rb.w & 0xFFFF0000u);
-            }
+            a.x += rres[8 * it]; a.y += rres[8 * it + 1]; a.z += rres[8 * it + 2]; a.w += rres[8 * it + 3];
+            b4.x += rres[8 * it + 4]; b4.y += rres[8 * it + 5]; b4.z += rres[8 * it + 6]; b4.w += rres[8 * it + 7];
           }
           uint4 w;
           w.x = pack_bf16x2(a.x, a.y);

@@ -106,6 +106,14 @@ int fwb_attn_fwd_partial(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const f
                          fwb_stream_t stream);
 int fwb_attn_merge(const float* part, const float* lse, const fwb_tensor4_t* out, int S, int B, int H, int L, int D,
                    fwb_stream_t stream);
+/* Why there is no `fwb_attn_fwd_sp(..., ncclComm_t, kv_chunks)` / `fwb_allgather_kv` entry point (SURVEY §8b lists them as an
+ * option): the exchange itself is ONE NCCL all-gather of the packed K|V rows per attention, and the host side of this path is
+ * PyTorch (north star), which already owns the NCCL communicator (ProcessGroupNCCL, one per process / GPU).  Pulling a raw
+ * ncclComm_t through a C ABI would either duplicate that communicator (a second NVLS / ring set-up per process and a second
+ * stream-ordering domain) or reach into torch internals.  So the collective is issued by the host layer on a side stream
+ * (fwb200/sp.py: all_gather_into_tensor in `kv_chunks` row slices) and what the ABI exports is the compute half of the
+ * pipeline: fwb_attn_fwd_partial consumes slice c while slice c+1 is in flight, fwb_attn_merge combines the slices.  The pair
+ * (host all-gather slice, fwb_attn_fwd_partial) is the `attn_fwd_sp` of the survey, split at the library boundary. */
 
 /* Tuning / test hooks (process-wide; one process drives one GPU).  None of them changes what is computed beyond fp32
  * re-association or the sub-bf16 error of the exp2 polynomial; they select between measured kernel variants.

@@ -167,7 +167,7 @@ def ref_joint(tmp_path_factory):
     if not _staged():
         pytest.skip("reference not staged")
     d = tmp_path_factory.mktemp("ref_joint")
-    rep = _run_ref(["joint", "--device", "cuda", "--grid", *GRID, "--text-len", TEXT_LEN, "--modes", "bf16_fa2,fp32", "--out", d,
+    rep = _run_ref(["joint", "--device", "cuda", "--grid", *GRID, "--text-len", TEXT_LEN, "--modes", "bf16_fa2,bf16_sdpa,fp32", "--out", d,
                     "--pcb", JOINT["pcb"], "--irg", JOINT["irg"], "--heads", "--head-layers", 3, 2, 1, 0])
     REPORT["reference_run_joint"] = rep
     return rep, d
@@ -195,7 +195,10 @@ def test_reduced_joint_forward_with_heads_at_c2_vs_reference_cuda_bf16(ref_joint
     ref = torch.load(d / "joint_bf16_fa2.pt")
     gold = torch.load(d / "joint_fp32.pt")
     assert out.shape == ref["out"].shape == (1, 16, f, 2 * h, 2 * w) and out.dtype == ref["out"].dtype
-    check("joint/latent_out", out.cpu(), ref["out"], None, gold["out"], 0.35)
+    sdpa = torch.load(d / "joint_bf16_sdpa.pt")
+    # after 4 DiT blocks + head the bf16 roundings of two correct implementations have decorrelated: ~27 % bit-equal elements,
+    # the same as between the reference's own flash-attn and SDPA runs (yardstick); the floor sits below both
+    check("joint/latent_out", out.cpu(), ref["out"], sdpa["out"], gold["out"], 0.20)
     assert set(pred) == set(ref["pred"]), (sorted(pred), sorted(ref["pred"]))
     for k in sorted(ref["pred"]):                       # depth, depth_conf, world_points, world_points_conf, pose_enc
         assert pred[k].shape == ref["pred"][k].shape, (k, pred[k].shape, ref["pred"][k].shape)
