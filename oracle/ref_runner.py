@@ -13,6 +13,7 @@ Commands
   joint   reduced-depth FantasyWorldFusionModel.joint_forward (model_wan21.py:104-224), optional geometry heads.
   step    K denoise steps = 2 x joint_forward + CFG + FlowMatchScheduler.step, exactly the loop body of
           model_wan21.py:289-322, timed (CUDA events on the GPU, perf_counter on the CPU).
+  schema  state_dict key -> shape of the fusion model at a given depth (meta device), for the drop-in schema test.
 Modes (precision / attention backend)
   bf16_fa2   model.to(bf16) + torch.autocast(bf16)  (inference_wan21.py:224, :310), flash_attention() -> flash_attn_func
   bf16_sdpa  same with FLASH_ATTN_2_AVAILABLE cleared -> F.scaled_dot_product_attention (wan_video_dit.py:60-65)
@@ -273,9 +274,21 @@ def cmd_step(a):
                       "max_mem_gib": mem, "threads": torch.get_num_threads(), "finite": bool(torch.isfinite(lat.float()).all())}))
 
 
+def cmd_schema(a):
+    """state_dict key -> shape of the reference fusion model at the given depth, built on the meta device (no storage)."""
+    with torch.device("meta"):
+        model, ns = shim.build_reference_fusion(num_dit_layers=a.pcb + a.irg, start_index=a.pcb, heads=True, flash_attn=False, dtype=None)
+    schema = {k: list(v.shape) for k, v in model.state_dict().items()}
+    if a.out:
+        Path(a.out).write_text(json.dumps(schema))
+    import hashlib
+    digest = hashlib.sha256(json.dumps(sorted(schema.items())).encode()).hexdigest()
+    print(json.dumps({"cmd": "schema", "pcb": a.pcb, "irg": a.irg, "keys": len(schema), "sha256": digest}))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("cmd", choices=["blocks", "joint", "step"])
+    ap.add_argument("cmd", choices=["blocks", "joint", "step", "schema"])
     ap.add_argument("--device", default="cuda" if torch.cuda.is_available() else "cpu")
     ap.add_argument("--grid", type=int, nargs=3, default=[1, 4, 4])
     ap.add_argument("--text-len", type=int, default=512)
@@ -301,7 +314,7 @@ def main():
     import io
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
-        {"blocks": cmd_blocks, "joint": cmd_joint, "step": cmd_step}[a.cmd](a)
+        {"blocks": cmd_blocks, "joint": cmd_joint, "step": cmd_step, "schema": cmd_schema}[a.cmd](a)
     os.write(real_stdout, buf.getvalue().strip().splitlines()[-1].encode() + b"\n")
 
 

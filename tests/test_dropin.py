@@ -1,0 +1,111 @@
+"""Drop-in surface: (1) every `FantasyWorld.*` import the reference CLIs perform resolves against
+the mirror package and yields the named objects; (2) the FULL-depth model (16 PCB + 24 IRG, heads) has exactly the reference's
+state_dict schema (3132 keys) — so the released `model.pth` loads with no missing / unexpected keys (inference_wan21.py:215-220).
+The reference side comes from the staged copy (oracle/_ref, oracle/make_ref.py) in its own process; a committed digest pins the
+schema where no reference is staged."""
+import ast
+import hashlib
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+REF_ROOTS = [Path("/root/reference"), ROOT / "oracle" / "_ref"]
+FULL_SCHEMA_SHA256 = "00e3ba3a81647252f5a9ccac297d6bf44b332c554164914219d7942132082606"   # reference, 16 PCB + 24 IRG, heads: 3132 keys
+FULL_SCHEMA_KEYS = 3132
+
+
+def _ref_root():
+    for r in REF_ROOTS:
+        if (r / "inference_wan21.py").exists():
+            return r
+    return None
+
+
+def _mirror_full_schema():
+    from fwb200.synth import CAMERA_CFG, VGGT_CFG, WAN21_I2V_14B
+    from FantasyWorld.fusion.model_wan21 import FantasyWorldFusionModel
+    with torch.device("meta"):
+        m = FantasyWorldFusionModel(start_index=16, use_gradient_checkpointing=False, cross_attention_list=list(range(24)), dit_path=None,
+                                    vggt_cfg=dict(VGGT_CFG), camera_control=True, camera_cfg=dict(CAMERA_CFG), dit_config=dict(WAN21_I2V_14B))
+    return {k: list(v.shape) for k, v in m.state_dict().items()}
+
+
+def test_full_depth_state_dict_schema_is_the_reference_one(tmp_path):
+    ours = _mirror_full_schema()
+    assert len(ours) == FULL_SCHEMA_KEYS
+    assert hashlib.sha256(json.dumps(sorted(ours.items())).encode()).hexdigest() == FULL_SCHEMA_SHA256
+    if _ref_root() is None:
+        return
+    out = tmp_path / "schema.json"
+    r = subprocess.run([sys.executable, str(ROOT / "oracle" / "ref_runner.py"), "schema", "--pcb", "16", "--irg", "24", "--out", str(out)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = json.loads(out.read_text())
+    assert json.loads(r.stdout.strip().splitlines()[-1])["sha256"] == FULL_SCHEMA_SHA256     # the pinned digest IS the reference's
+    assert set(ours) == set(ref), (sorted(set(ours) ^ set(ref))[:10])
+    assert ours == ref
+    # the surgery leaves Identity behind exactly where the reference does (model_wan21.py:74-75)
+    assert not any(k.startswith(("pipe.dit.blocks.16.", "pipe.dit.blocks.39.", "vggt.aggregator.global_blocks.")) for k in ours)
+
+
+@pytest.mark.parametrize("cli", ["inference_wan21.py", "inference_wan22.py"])
+def test_reference_cli_import_block_resolves_against_the_mirror(cli):
+    root = _ref_root()
+    if root is None:
+        pytest.skip("reference CLI not staged (python oracle/make_ref.py)")
+    tree = ast.parse((root / cli).read_text())
+    checked = 0
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ImportFrom) and node.module and node.module.startswith("FantasyWorld"):
+            if any(part in node.module for part in ("prompters", "data", "vram_management", "text_encoder", "image_encoder", "wan_video_vae")):
+                continue        # once-per-sample front-end that stays with the reference
+            mod = __import__(node.module, fromlist=[a.name for a in node.names])
+            assert str(Path(mod.__file__).resolve()).startswith(str(ROOT / "fantasy-world_b200")), (node.module, mod.__file__)
+            for alias in node.names:
+                assert hasattr(mod, alias.name), f"{cli}: from {node.module} import {alias.name}"
+                checked += 1
+    assert checked >= 2, checked
+
+
+def test_pose_encoding_helpers_match_reference():
+    """FantasyWorld.vggt.utils.{pose_enc, rotation} (imported by both reference CLIs): the mirror against the reference's own
+    functions on random and degenerate (180 degree) rotations, plus the encode -> decode round trip."""
+    import importlib
+    import importlib.util
+    from FantasyWorld.vggt.utils import pose_enc as mine
+    from FantasyWorld.vggt.utils.rotation import mat_to_quat, quat_to_mat
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(2, 37, 4, generator=g, dtype=torch.float64)
+    q[0, :6] = torch.tensor([[1.0, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1], [1, 1, 0, 0], [0.6, 0, 0.8, 1e-9]], dtype=torch.float64)
+    R = quat_to_mat(q)
+    assert torch.allclose(R @ R.transpose(-1, -2), torch.eye(3, dtype=torch.float64).expand_as(R), atol=1e-12)
+    q2 = mat_to_quat(R)
+    assert (q2[..., 3] >= 0).all() and torch.allclose(quat_to_mat(q2), R, atol=1e-9)
+    ext = torch.cat([R, torch.randn(2, 37, 3, 1, generator=g, dtype=torch.float64)], dim=-1)
+    K = torch.zeros(2, 37, 3, 3, dtype=torch.float64)
+    K[..., 0, 0], K[..., 1, 1], K[..., 0, 2], K[..., 1, 2], K[..., 2, 2] = 500.0, 450.0, 416.0, 240.0, 1.0
+    enc = mine.extri_intri_to_pose_encoding(ext, K, (480, 832))
+    assert enc.shape == (2, 37, 9) and enc.dtype == torch.float32
+    e2, k2 = mine.pose_encoding_to_extri_intri(enc.double(), (480, 832))
+    assert torch.allclose(e2, ext, atol=1e-5) and torch.allclose(k2, K, atol=1e-3)
+    root = _ref_root()
+    if root is None:
+        return
+    d = root / "FantasyWorld" / "vggt" / "utils"
+    spec = importlib.util.spec_from_file_location("fwb_ref_vggt_utils", d / "__init__.py", submodule_search_locations=[str(d)])
+    pkg = importlib.util.module_from_spec(spec)
+    sys.modules["fwb_ref_vggt_utils"] = pkg
+    spec.loader.exec_module(pkg)
+    ref = importlib.import_module("fwb_ref_vggt_utils.pose_enc")
+    ref_rot = importlib.import_module("fwb_ref_vggt_utils.rotation")
+    assert torch.allclose(q2, ref_rot.mat_to_quat(R), atol=1e-12)
+    assert torch.allclose(R, ref_rot.quat_to_mat(q), atol=1e-12)
+    assert torch.equal(enc, ref.extri_intri_to_pose_encoding(ext, K, (480, 832)))
+    re, rk = ref.pose_encoding_to_extri_intri(enc, (480, 832))
+    me, mk = mine.pose_encoding_to_extri_intri(enc, (480, 832))
+    assert torch.equal(me, re) and torch.equal(mk, rk)
