@@ -2,6 +2,9 @@
 # GPU call C (1 GPU): attention timeline traces (poly 0 / 2 / 3), GEMM correctness after the epilogue change, per-kernel step
 # breakdown, vggt_only workload, joint parity rerun
 mkdir -p gpurun_out
+(timeout 400 python -m pytest tests/test_gpu_ops.py -x -q -k "attention" 2>&1 | tail -6)
+timeout 300 python tools/gpu_attn_sweep.py 2>&1 | tail -60
+timeout 120 python tools/attn_trace.py run 3 2 2>&1 | tail -16
 for P in 0 2 3; do timeout 120 python tools/attn_trace.py run 1 $P 2>&1 | tail -16; done
 timeout 120 python tools/attn_trace.py run 2 2 2>&1 | tail -16
 (timeout 600 python -m pytest tests/test_gpu_ops.py -x -q -k "gemm or linear" 2>&1 | tail -5)

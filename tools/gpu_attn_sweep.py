@@ -2,8 +2,7 @@
 
     python tools/gpu_attn_sweep.py [--quick]
 
-For every shape: kernel variant (1 = S/P aliased, 2 = decoupled) x exp2-polynomial share (0, 2, 3, 4 pairs of 8) [x MUFU ping-pong
-for the aliased kernel], 3 interleaved rounds each (the box runs power-capped: +-4 % between rounds), plus cuDNN / flash SDPA of
+For every shape: kernel variant (1 = S/P aliased, 2 = decoupled, 3 = decoupled + software-pipelined softmax) x exp2-polynomial share (pairs of 8), 3 interleaved rounds each (the box runs power-capped: +-4 % between rounds), plus cuDNN / flash SDPA of
 torch on the same tensors.  Writes gpurun_out/r02_attn_sweep.log (TFLOP/s = 4 B H Lq Lk D / time)."""
 import sys
 from pathlib import Path
@@ -47,14 +46,15 @@ for (B, H, Lq, Lk, D, name) in SHAPES:
     q, k, v = (torch.randn(B, L, H, D, device="cuda").to(torch.bfloat16) for L in (Lq, Lk, Lk))
     o = torch.empty_like(q)
     fl = 4.0 * B * H * Lq * Lk * D
-    configs = [(var, poly, pp) for var in (1, 2) for poly in (0, 2, 3, 4) for pp in ((0, 1) if var == 1 else (1,))]
+    configs = [(1, 0, 0), (1, 2, 0), (2, 0, 1), (2, 2, 1), (3, 0, 0), (3, 2, 0), (3, 3, 0)]
     res = {c: [] for c in configs}
     for rnd in range(3):
         for c in configs:
             var, poly, pp = c
             lib.fwb_attn_set_variant(var)
             lib.fwb_attn_set_exp2_poly(poly)
-            lib.fwb_attn_set_mufu_pingpong(var, pp)
+            if var in (1, 2):
+                lib.fwb_attn_set_mufu_pingpong(var, pp)
             res[c].append(fl / timeit(lambda: fwb200.attention(q, k, v, out=o)) / 1e9)
     lib.fwb_attn_set_variant(0)
     lib.fwb_attn_set_exp2_poly(-1)
