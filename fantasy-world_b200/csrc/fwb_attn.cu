@@ -734,7 +734,11 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       const uint32_t o_tmem = tmem_base + Cfg::kColO + i * D;
 
       mbar_wait(&q_full[i], 0);
-      for (int j = 0; j <= n_kv; ++j) {
+      // QK runs LA tiles ahead of PV in this warp's (in-order) program.  Classic softmax: 1 — S(j+1) is wanted when tile j's
+      // exponentials are done.  Pipelined softmax: 2 — S(j+1) is pulled out of TMEM at the START of tile j, so QK(j+1) has to be
+      // issued when S(j) leaves TMEM in the middle of tile j-1, i.e. ahead of PV(j-1), which only becomes ready at its end.
+      constexpr int LA = PIPE ? 2 : 1;
+      for (int j = 0; j < n_kv + LA; ++j) {
         if (j < n_kv) {
           // S_i(j) = Q_i K_j^T  — needs the softmax to have pulled S_i(j-1) into registers
           const uint32_t ks = j % ST;
@@ -750,9 +754,9 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           tc_commit(&k_empty[ks]);
           TRACE1(8 + 0, j, i * 3 + 0);
         }
-        if (j > 0) {
-          // O_i += P_i(j-1) V_(j-1)
-          const int jj = j - 1;
+        if (j >= LA) {
+          // O_i += P_i(j-LA) V_(j-LA)
+          const int jj = j - LA;
           const uint32_t vs = jj % ST;
           mbar_wait(&p_full[i], jj & 1);
           mbar_wait(&v_full[vs], (jj / ST) & 1);
