@@ -173,38 +173,6 @@ __device__ __forceinline__ float softmax_exp(const uint32_t (&v)[N], float sl2, 
   return s0 + s1;
 }
 
-// One pair of softmax_exp (see above): p = 2^(v * sl2 - m) for two adjacent elements, accumulated and packed.
-template <int POLY>
-__device__ __forceinline__ void softmax_exp_pair(int pair, uint32_t v0, uint32_t v1, uint64_t S2, uint64_t M2, uint64_t& acc, uint32_t& pk) {
-  const uint64_t MAGIC = pack2(12582912.f, 12582912.f);
-  const uint64_t C3 = pack2(0.07706704f, 0.07706704f), C2 = pack2(0.22764499f, 0.22764499f), C1 = pack2(0.69511679f, 0.69511679f),
-                 C0 = pack2(1.0f, 1.0f);
-  uint64_t x = ffma2(pack2(__uint_as_float(v0), __uint_as_float(v1)), S2, M2);
-  float p0, p1;
-  if (POLY > 0 && ((pair & 7) * POLY) % 8 < POLY) {
-    float x0, x1;
-    unpack2(x, x0, x1);
-    x = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
-    const uint64_t r = fadd2_rm(x, MAGIC);
-    const uint64_t f = fsub2(x, fsub2(r, MAGIC));
-    uint64_t q = ffma2(f, C3, C2);
-    q = ffma2(q, f, C1);
-    q = ffma2(q, f, C0);
-    float q0, q1, r0, r1;
-    unpack2(q, q0, q1);
-    unpack2(r, r0, r1);
-    p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(r0) << 23));
-    p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23));
-  } else {
-    float x0, x1;
-    unpack2(x, x0, x1);
-    p0 = fast_exp2(x0);
-    p1 = fast_exp2(x1);
-  }
-  acc = fadd2(acc, pack2(p0, p1));
-  pk = pack_bf16x2(p0, p1);
-}
-
 template <int D, int POLY>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -602,12 +570,6 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
 // columns), head_dim 128 -> BKV 64 (448 columns).  K/V stages are released by both MMA warps (mbarrier count 2).
 // =====================================================================================================================
 constexpr int kAttn2Threads = 352;
-constexpr int kAttn3Threads = 384;   // pipelined-softmax variant: a 12th (idle) warp completes the third warpgroup, so that the two
-                                     // softmax warpgroups can take registers from it with setmaxnreg (two S tiles live per thread)
-template <int N>
-__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N>
-__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ int g_attn2_pingpong = 1;   // exp2 phases of the two Q tiles alternate through named barriers (fwb_attn_set_mufu_pingpong(2, .))
 
 template <int D, int BK>
@@ -625,8 +587,8 @@ struct Attn2Cfg {
   static_assert(2 * D + 2 * kTileCols <= 512, "TMEM overflow");
 };
 
-template <int D, int BK, int POLY, bool PIPE>
-__global__ void __launch_bounds__(PIPE ? kAttn3Threads : kAttn2Threads, 1)
+template <int D, int BK, int POLY>
+__global__ void __launch_bounds__(kAttn2Threads, 1)
 attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
              const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   using Cfg = Attn2Cfg<D, BK>;
@@ -694,13 +656,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp >= 8) {
-  // register re-partition of the pipelined variant (inside the role branches, so that the compiler knows each region's budget):
-  // 168 per thread at launch -> 216 for the two softmax warpgroups, 64 for this one
-  if constexpr (PIPE) setmaxnreg_dec<64>();
-  if (warp == 11) {
-    // idle warp of the pipelined variant (warpgroup filler)
-  } else if (warp == 10) {
+  if (warp == 10) {
     // ------------------------------------ TMA producer ------------------------------------
     if (elect_one()) {
       for (int i = 0; i < 2; ++i) {
@@ -734,11 +690,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       const uint32_t o_tmem = tmem_base + Cfg::kColO + i * D;
 
       mbar_wait(&q_full[i], 0);
-      // QK runs LA tiles ahead of PV in this warp's (in-order) program.  Classic softmax: 1 — S(j+1) is wanted when tile j's
-      // exponentials are done.  Pipelined softmax: 2 — S(j+1) is pulled out of TMEM at the START of tile j, so QK(j+1) has to be
-      // issued when S(j) leaves TMEM in the middle of tile j-1, i.e. ahead of PV(j-1), which only becomes ready at its end.
-      constexpr int LA = PIPE ? 2 : 1;
-      for (int j = 0; j < n_kv + LA; ++j) {
+      for (int j = 0; j <= n_kv; ++j) {
         if (j < n_kv) {
           // S_i(j) = Q_i K_j^T  — needs the softmax to have pulled S_i(j-1) into registers
           const uint32_t ks = j % ST;
@@ -754,9 +706,9 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
           tc_commit(&k_empty[ks]);
           TRACE1(8 + 0, j, i * 3 + 0);
         }
-        if (j >= LA) {
-          // O_i += P_i(j-LA) V_(j-LA)
-          const int jj = j - LA;
+        if (j > 0) {
+          // O_i += P_i(j-1) V_(j-1)
+          const int jj = j - 1;
           const uint32_t vs = jj % ST;
           mbar_wait(&p_full[i], jj & 1);
           mbar_wait(&v_full[vs], (jj / ST) & 1);
@@ -775,10 +727,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
         }
       }
     }
-  }
   } else {
     // ------------------------------------ softmax + epilogue ------------------------------
-    if constexpr (PIPE) setmaxnreg_inc<216>();
     const int i = warp >> 2;
     const uint32_t quad = warp & 3;
     const uint32_t lane_off = (quad * 32) << 16;
@@ -792,129 +742,10 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     // (4 lanes/clk: 8 clk per warp-wide ex2).  Left alone they fall into lock-step: the exp2 phases collide at half rate and
     // the MUFU idles while both do the row max and the TMEM traffic (tools/attn_trace.py).  Two named barriers per warp pair
     // make the exp2 phases alternate, so one tile's max / TMEM phase hides under the other's exponentials.
-    const bool pingpong = !PIPE && g_attn2_pingpong != 0;
+    const bool pingpong = g_attn2_pingpong != 0;
     const uint32_t bar_mine = 1 + quad + 4 * i, bar_other = 1 + quad + 4 * (1 - i);
     if (pingpong && i == 1) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");   // tile 0 goes first
 
-    if constexpr (PIPE) {
-      // ---- software-pipelined softmax (BK = 64): the exponentials of tile j run while S(j+1) is being pulled out of TMEM, and the
-      // row max of tile j+1 is folded into the second half of tile j's exponentials.  Nothing but MUFU / FMA work and the P
-      // hand-off is left on the per-tile chain of a softmax warp, the two warps that share an SM sub-partition stay in their
-      // exponential loops all the time (no distinct max / TMEM phase in which the MUFU would idle, hence no ping-pong barriers),
-      // and the tensor pipe runs QK(j+2) / PV(j) underneath.  Two S tiles are live in registers (2 x 64 + 32 packed P).
-      static_assert(!PIPE || BK == 64, "pipelined softmax: 64-key tiles");
-      const uint64_t S2 = pack2(sl2, sl2);
-      auto mask_ragged = [&](uint32_t (&t)[BK], int jj) {
-        if (jj == j_ragged) {
-          const int valid = p.Lk - (kv0 + jj) * BK;
-          if (valid < BK) {
-#pragma unroll
-            for (int c = 0; c < BK; ++c)
-              if (c >= valid) t[c] = 0xFF800000u;  // -inf
-          }
-        }
-      };
-      // decide the running max for the tile whose raw row max is `mx_raw`; rescales O / l when it grows by more than 2^8
-      auto settle_max = [&](float mx_raw, int jj) {
-        const float m_new = mx_raw * sl2;
-        const bool need = m_new > m_used + 8.0f;
-        if (__any_sync(0xffffffffu, need)) {
-          const float m_next = fmaxf(m_used, m_new);
-          const float alpha = fast_exp2(m_used - m_next);
-          l_sum *= alpha;
-          m_used = m_next;
-          if (jj > 0) {
-            mbar_wait(&p_free[i], (jj - 1) & 1);   // PV_i(jj-1) has completed: O_i is quiescent
-            tc_fence_after();
-#pragma unroll
-            for (int c0 = 0; c0 < D; c0 += 16) {
-              uint32_t o[16];
-              tmem_ld16(o_tmem + c0, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int c = 0; c < 16; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-              tmem_st16(o_tmem + c0, o);
-            }
-            tc_fence_before();
-          }
-        }
-      };
-      uint32_t va[BK], vb[BK];
-      // prologue: S(0) -> registers, its max
-      mbar_wait(&s_full[i], 0);
-      tc_fence_after();
-      tmem_ld32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&va[0]));
-      tmem_ld32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&va[32]));
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[i]);
-      mask_ragged(va, 0);
-      {
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < BK; c += 4) {
-          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(va[c]), __uint_as_float(va[c + 1])));
-          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(va[c + 2]), __uint_as_float(va[c + 3])));
-        }
-        settle_max(fmaxf(mx0, mx1), 0);
-      }
-      // one tile: exponentials of `cur` (tile j); `nxt` receives S(j+1)
-      auto tile = [&](uint32_t (&cur)[BK], uint32_t (&nxt)[BK], int j) {
-        const bool more = j + 1 < n_kv;
-        TRACE(warp, j, 0);
-        if (more) {
-          mbar_wait(&s_full[i], (j + 1) & 1);    // QK(j+1) was issued when S(j) left TMEM, one tile ago
-          tc_fence_after();
-          tmem_ld32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&nxt[0]));
-          tmem_ld32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&nxt[32]));
-        }
-        TRACE(warp, j, 1);
-        const uint64_t M2 = pack2(-m_used, -m_used);
-        uint64_t acc0 = pack2(0.f, 0.f), acc1 = pack2(0.f, 0.f);
-        uint32_t pk[BK / 2];
-#pragma unroll
-        for (int c = 0; c < BK / 2; c += 2) softmax_exp_pair<POLY>(c / 2, cur[c], cur[c + 1], S2, M2, (c & 2) ? acc1 : acc0, pk[c / 2]);
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-        if (more) {
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free[i]);   // S(j+1) is in registers: the MMA warp may issue QK(j+2)
-          mask_ragged(nxt, j + 1);
-        }
-        TRACE(warp, j, 2);
-#pragma unroll
-        for (int c = BK / 2; c < BK; c += 2) {
-          softmax_exp_pair<POLY>(c / 2, cur[c], cur[c + 1], S2, M2, (c & 2) ? acc1 : acc0, pk[c / 2]);
-          if (more) {   // 4 elements of the next tile's row max per pair of this tile's second half
-            const int e = (c - BK / 2) * 2;
-            mx0 = fmaxf(mx0, fmaxf(__uint_as_float(nxt[e]), __uint_as_float(nxt[e + 1])));
-            mx1 = fmaxf(mx1, fmaxf(__uint_as_float(nxt[e + 2]), __uint_as_float(nxt[e + 3])));
-          }
-        }
-        float s0, s1;
-        unpack2(fadd2(acc0, acc1), s0, s1);
-        l_sum += s0 + s1;
-        TRACE(warp, j, 3);
-        if (j > 0) {
-          mbar_wait(&p_free[i], (j - 1) & 1);     // PV_i(j-1) has finished reading P_i
-          tc_fence_after();
-        }
-        tmem_st32(p_tmem, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[i]);
-        TRACE(warp, j, 4);
-        if (more) settle_max(fmaxf(mx0, mx1), j + 1);
-        TRACE(warp, j, 5);
-      };
-      for (int j = 0; j < n_kv; j += 2) {
-        tile(va, vb, j);
-        if (j + 1 < n_kv) tile(vb, va, j + 1);
-      }
-    } else
     for (int j = 0; j < n_kv; ++j) {
       TRACE(warp, j, 0);
       mbar_wait(&s_full[i], j & 1);
@@ -1063,18 +894,18 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
-template <int D, int BK, int POLY, bool PIPE = false>
+template <int D, int BK, int POLY>
 int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B, int H,
                  cudaStream_t stream) {
   using Cfg = Attn2Cfg<D, BK>;
   static AttrOnce once;
   if (once.need(current_device()))
-    FWB_CUDA(cudaFuncSetAttribute(attn2_kernel<D, BK, POLY, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    FWB_CUDA(cudaFuncSetAttribute(attn2_kernel<D, BK, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const long long n_tiles = (long long)p.nq * H * B;
   const long long tail = n_tiles - p.n_full;
   const long long grid = p.n_full + (p.S > 1 ? tail * p.S : tail);
   FWB_CHECK(grid < (1ll << 31), "attn: grid too large");
-  attn2_kernel<D, BK, POLY, PIPE><<<(unsigned)grid, PIPE ? kAttn3Threads : kAttn2Threads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  attn2_kernel<D, BK, POLY><<<(unsigned)grid, kAttn2Threads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
   FWB_CUDA(cudaGetLastError());
   if (p.S > 1) {
     const long long total = tail * (2 * BQ) * (p.d_real / 8);
@@ -1084,36 +915,19 @@ int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap
   return FWB_OK;
 }
 
-// POLY (pairs out of every 8 that take 2^x from the FMA-pipe polynomial) is a template parameter: dispatch over the built values
+// POLY (pairs out of every 8 that take 2^x from the FMA-pipe polynomial) is a template parameter; built: 0 (MUFU only, the A/B
+// reference) and 2 (the measured optimum, default).  3/8 and 4/8 were measured slower (profiles/r02_attention.md) and are not built.
 template <int D>
 int launch_attn_poly(int poly, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
                      int H, cudaStream_t stream) {
-  switch (poly) {
-    case 2: return launch_attn<D, 2>(tq, tk, tv, p, B, H, stream);
-    case 3: return launch_attn<D, 3>(tq, tk, tv, p, B, H, stream);
-    case 4: return launch_attn<D, 4>(tq, tk, tv, p, B, H, stream);
-    default: return launch_attn<D, 0>(tq, tk, tv, p, B, H, stream);
-  }
-}
-// variant 3: the decoupled kernel with the software-pipelined softmax, 64-key tiles (poly 0 / 2 / 3 built)
-template <int D>
-int launch_attn3_poly(int poly, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
-                      int H, cudaStream_t stream) {
-  switch (poly) {
-    case 2: return launch_attn2<D, 64, 2, true>(tq, tk, tv, p, B, H, stream);
-    case 3: return launch_attn2<D, 64, 3, true>(tq, tk, tv, p, B, H, stream);
-    default: return launch_attn2<D, 64, 0, true>(tq, tk, tv, p, B, H, stream);
-  }
+  if (poly == 2) return launch_attn<D, 2>(tq, tk, tv, p, B, H, stream);
+  return launch_attn<D, 0>(tq, tk, tv, p, B, H, stream);
 }
 template <int D, int BK>
 int launch_attn2_poly(int poly, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B,
                       int H, cudaStream_t stream) {
-  switch (poly) {
-    case 2: return launch_attn2<D, BK, 2>(tq, tk, tv, p, B, H, stream);
-    case 3: return launch_attn2<D, BK, 3>(tq, tk, tv, p, B, H, stream);
-    case 4: return launch_attn2<D, BK, 4>(tq, tk, tv, p, B, H, stream);
-    default: return launch_attn2<D, BK, 0>(tq, tk, tv, p, B, H, stream);
-  }
+  if (poly == 2) return launch_attn2<D, BK, 2>(tq, tk, tv, p, B, H, stream);
+  return launch_attn2<D, BK, 0>(tq, tk, tv, p, B, H, stream);
 }
 
 // out[b,l,h,:] = sum_s w_s part[s][b,l,h,:] / sum_s w_s,  w_s = 2^(lse[s][b,h,l] - max_s lse)   (fp32 in, bf16 out)
@@ -1207,7 +1021,7 @@ extern "C" int fwb_attn_trace_read(long long* host_out, int cta) {
 #endif
 
 extern "C" int fwb_attn_set_variant(int variant) {
-  FWB_CHECK(variant >= 0 && variant <= 3, "attn_set_variant: 0 (default per head_dim), 1 (v1), 2 (decoupled) or 3 (decoupled, pipelined softmax)");
+  FWB_CHECK(variant >= 0 && variant <= 2, "attn_set_variant: 0 (default per head_dim), 1 (aliased S/P) or 2 (decoupled S/P)");
   g_attn_variant = variant;
   return FWB_OK;
 }
@@ -1218,8 +1032,7 @@ extern "C" int fwb_attn_set_tail_split(int enabled) {
 }
 
 extern "C" int fwb_attn_set_exp2_poly(int pairs_of_8) {
-  FWB_CHECK(pairs_of_8 == -1 || pairs_of_8 == 0 || (pairs_of_8 >= 2 && pairs_of_8 <= 4),
-            "attn_set_exp2_poly: -1 (default), 0, 2, 3 or 4 pairs out of every 8");
+  FWB_CHECK(pairs_of_8 == -1 || pairs_of_8 == 0 || pairs_of_8 == 2, "attn_set_exp2_poly: -1 (default), 0 or 2 pairs out of every 8");
   g_attn_poly = pairs_of_8;
   return FWB_OK;
 }
@@ -1290,7 +1103,7 @@ static int attn_impl(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_t
   int rc;
   if ((rc = make_qkv_map(&tq, q, B, H, Lq, D))) return rc;
   const int variant = g_attn_variant ? g_attn_variant : (D == 64 ? 2 : 1);
-  const int bk = (variant == 3) ? 64 : (variant == 2) ? (D == 64 ? 128 : 64) : BKV;     // keys per KV tile of the kernel that will run
+  const int bk = (variant == 2) ? (D == 64 ? 128 : 64) : BKV;     // keys per KV tile of the kernel that will run
   if ((rc = make_qkv_map(&tk, k, B, H, Lk, D, bk))) return rc;
   if ((rc = make_qkv_map(&tv, v, B, H, Lk, D, bk))) return rc;
   AttnParams p;
@@ -1322,10 +1135,6 @@ static int attn_impl(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_t
     }
   }
   const int poly = g_attn_poly >= 0 ? g_attn_poly : default_poly(D);
-  if (variant == 3) {
-    if (D == 64) return launch_attn3_poly<64>(poly, tq, tk, tv, p, B, H, stream);
-    return launch_attn3_poly<128>(poly, tq, tk, tv, p, B, H, stream);
-  }
   if (variant == 2) {
     if (D == 64) return launch_attn2_poly<64, 128>(poly, tq, tk, tv, p, B, H, stream);
     return launch_attn2_poly<128, 64>(poly, tq, tk, tv, p, B, H, stream);

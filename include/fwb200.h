@@ -117,12 +117,11 @@ int fwb_attn_merge(const float* part, const float* lse, const fwb_tensor4_t* out
 
 /* Tuning / test hooks (process-wide; one process drives one GPU).  None of them changes what is computed beyond fp32
  * re-association or the sub-bf16 error of the exp2 polynomial; they select between measured kernel variants.
- *   fwb_attn_set_variant        0 = default per head_dim; 1 = aliased S/P kernel, 2 = decoupled S/P kernel, 3 = decoupled with the
- *                               software-pipelined softmax (64-key tiles)
+ *   fwb_attn_set_variant        0 = default per head_dim (64 -> decoupled S/P kernel, 96 / 128 -> aliased S/P kernel), 1 / 2 = force
  *   fwb_attn_set_tail_split     key-split tail of the tile schedule on (1, default) / off (0)
  *   fwb_attn_set_exp2_poly      pairs out of every 8 softmax element pairs whose 2^x comes from the packed FMA-pipe polynomial
- *                               instead of MUFU.EX2: -1 = default per head_dim, 0, 2, 3, 4 (max rel. error 8.6e-5 before P is
- *                               rounded to bf16)
+ *                               instead of MUFU.EX2: -1 = default (2), 0 = MUFU only, 2 (max rel. error 8.6e-5 before P is rounded
+ *                               to bf16; larger shares were measured slower and are not built)
  *   fwb_attn_set_mufu_pingpong  kernel 1 (aliased) / 2 (decoupled): alternate the exp2 phases of the two Q tiles of a CTA */
 int fwb_attn_set_variant(int variant);
 int fwb_attn_set_tail_split(int enabled);

@@ -204,14 +204,13 @@ def test_attention_tail_split_matches_unsplit(fwb, B, H, Lq, Lk, D):
     torch.testing.assert_close(out[:, rows].float(), _attn_ref(q[:, rows], k, v), rtol=2e-2, atol=6e-3)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("B,H,Lq,Lk,D", [(1, 3, 1000, 777, 128), (2, 4, 300, 1300, 64), (1, 12, 1560, 1565, 96), (1, 2, 129, 1, 128),
                                          (1, 2, 257, 65, 128), (1, 2, 300, 128, 64),
                                          (1, 8, 4095, 8190, 128), (3, 16, 1565, 1565, 64)])
 def test_attention_kernel_variants(fwb, variant, B, H, Lq, Lk, D):
-    """All attention kernels (1: P aliased on S, one MMA thread; 2: decoupled S / P, one MMA warp per Q tile, MUFU ping-pong;
-    3: decoupled with the software-pipelined softmax, 64-key tiles) against fp32 math, including the split-KV outputs.  The
-    default picks one per head_dim; all stay covered."""
+    """Both attention kernels (1: P aliased on S, one MMA thread; 2: decoupled S / P, one MMA warp per Q tile, MUFU ping-pong)
+    against fp32 math, including the split-KV outputs.  The default picks one per head_dim; both stay covered."""
     torch.manual_seed(variant * 7 + Lq + Lk + D)
     q, k, v = (_bf(torch.randn(B, L, H, D, device="cuda")) for L in (Lq, Lk, Lk))
     part = torch.empty(1, B, Lq, H, D, device="cuda")
@@ -231,8 +230,8 @@ def test_attention_kernel_variants(fwb, variant, B, H, Lq, Lk, D):
     torch.testing.assert_close(lse[0], torch.logsumexp(s, dim=-1) / math.log(2), rtol=1e-4, atol=2e-3)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
-@pytest.mark.parametrize("poly", [2, 3])
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("poly", [2])
 @pytest.mark.parametrize("B,H,Lq,Lk,D", [(1, 3, 1000, 3000, 128), (1, 12, 1560, 1565, 96), (2, 4, 300, 1300, 64)])
 def test_attention_exp2_polynomial_share(fwb, variant, poly, B, H, Lq, Lk, D):
     """fwb_attn_set_exp2_poly: `poly` of every 8 softmax element pairs take 2^x from the packed FMA-pipe polynomial (max rel. error

@@ -2,7 +2,7 @@
 
     python tools/gpu_attn_sweep.py [--quick]
 
-For every shape: kernel variant (1 = S/P aliased, 2 = decoupled, 3 = decoupled + software-pipelined softmax) x exp2-polynomial share (pairs of 8), 3 interleaved rounds each (the box runs power-capped: +-4 % between rounds), plus cuDNN / flash SDPA of
+For every shape: kernel variant (1 = S/P aliased, 2 = decoupled) x exp2-polynomial share (0 or 2 pairs of 8) x MUFU ping-pong, 3 interleaved rounds each (the box runs power-capped: +-4 % between rounds), plus cuDNN / flash SDPA of
 torch on the same tensors.  Writes gpurun_out/r02_attn_sweep.log (TFLOP/s = 4 B H Lq Lk D / time)."""
 import sys
 from pathlib import Path
@@ -46,7 +46,7 @@ for (B, H, Lq, Lk, D, name) in SHAPES:
     q, k, v = (torch.randn(B, L, H, D, device="cuda").to(torch.bfloat16) for L in (Lq, Lk, Lk))
     o = torch.empty_like(q)
     fl = 4.0 * B * H * Lq * Lk * D
-    configs = [(1, 0, 0), (1, 2, 0), (2, 0, 1), (2, 2, 1), (3, 0, 0), (3, 2, 0), (3, 3, 0)]
+    configs = [(1, 0, 0), (1, 2, 0), (1, 2, 1), (2, 0, 1), (2, 2, 1), (2, 2, 0)]
     res = {c: [] for c in configs}
     for rnd in range(3):
         for c in configs:
