@@ -1,8 +1,9 @@
 """Minimal stand-in for FantasyWorld/diffsynth_wan21/pipelines/wan_video.py: the attribute surface
 FantasyWorldFusionModel and inference_wan21.py touch (`dit`, `scheduler`, `device`, `torch_dtype`, `generate_noise`,
-`prepare_extra_input`, `load_models_to_device`).  The conditioning encoders and the VAE (`encode_prompt`,
-`encode_image`, `vae`) run once per sample outside the denoising loop and are out of scope for this hot-path build
-(SURVEY §2, §8f N1/N3): they raise with a clear message instead of silently doing something else.
+`prepare_extra_input`, `load_models_to_device`, `vae`).  The VAE (`pipe.vae.decode(..., tiled=True)`) is the
+mirror in ..models.wan_video_vae (attach with `enable_vae()` or by loading a checkpoint through the model manager).  The text /
+image encoders (`encode_prompt`, `encode_image`: T5, CLIP) run once per sample outside the denoising loop and stay with the
+reference: they raise with a clear message instead of silently doing something else.
 """
 from __future__ import annotations
 
@@ -29,6 +30,15 @@ class WanVideoPipeline(nn.Module):
         pipe = WanVideoPipeline(device=device or model_manager.device, torch_dtype=torch_dtype or model_manager.torch_dtype)
         pipe.dit = model_manager.fetch_model("wan_video_dit")
         return pipe
+
+    def enable_vae(self, z_dim: int = 16, state_dict=None, device=None, dtype=None):
+        """Attach the Wan VAE mirror (random-init unless a state_dict with the reference's `model.*` keys is given)."""
+        from ..models.wan_video_vae import WanVideoVAE
+        self.vae = WanVideoVAE(z_dim=z_dim)
+        if state_dict is not None:
+            self.vae.load_state_dict(state_dict, strict=True)
+        self.vae.to(device=device or self.device, dtype=dtype or self.torch_dtype)
+        return self.vae
 
     def generate_noise(self, shape, seed=None, device="cpu", dtype=torch.float16):
         gen = None if seed is None else torch.Generator(device).manual_seed(seed)

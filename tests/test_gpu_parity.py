@@ -296,3 +296,40 @@ def test_geometry_heads_index_exact_on_cuda():
     for (n, _, v), (_, _, gv) in zip(rec, gold_rec):
         if gv is not None:
             assert torch.equal(v, gv), n
+
+
+def test_tiled_vae_decode_at_c2_size_on_cuda():
+    """SURVEY §8f N1 on the GPU: the call inference_wan21.py:324-330 makes after the sampler — 21 latent frames of 60x104, tile
+    (30, 52), stride (15, 26) -> 81 frames of 480x832 in [-1, 1]; fp32 vs the CPU golden-pinned math on a small case, and the
+    bf16 full-size run finite with the right shape."""
+    import time
+    from _common import gold
+    from FantasyWorld.diffsynth_wan21.pipelines.wan_video import WanVideoPipeline
+    from fwb_synth import synth_init
+    g = gold("vae.pt")
+    pipe = WanVideoPipeline(device="cuda", torch_dtype=torch.bfloat16)
+    vae = pipe.enable_vae(dtype=torch.float32)
+    wrap = torch.nn.Module()
+    wrap.vae = vae
+    vae.model.requires_grad_(True)
+    synth_init(wrap, seed=0, gen_device="cpu")
+    vae.model.requires_grad_(False)
+    z = torch.randn(1, 16, 3, 6, 8, generator=torch.Generator().manual_seed(11))
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            tiled = vae.decode(z.cuda(), device="cuda", tiled=True, tile_size=g["tile_size"], tile_stride=g["tile_stride"])
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert rel_err(tiled.cpu(), g["tiled"]) < 1e-4, rel_err(tiled.cpu(), g["tiled"])
+    vae.to(torch.bfloat16)
+    lat = torch.randn(1, 16, 21, 60, 104, device="cuda", dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        video = vae.decode(lat, device="cuda", tiled=True, tile_size=(30, 52), tile_stride=(15, 26))
+    torch.cuda.synchronize()
+    print(f"tiled VAE decode 81x480x832 on B200: {time.perf_counter() - t0:.2f} s (9 tiles, whole-clip convolutions)")
+    assert video.shape == (1, 3, 81, 480, 832) and torch.isfinite(video.float()).all()
+    assert float(video.max()) <= 1.0 and float(video.min()) >= -1.0
