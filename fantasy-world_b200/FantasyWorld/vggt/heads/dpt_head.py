@@ -1,6 +1,7 @@
 """Mirror of FantasyWorld/vggt/heads/dpt_head.py (reference): DPT dense-prediction head with a causal 4x temporal
 up-sampler (21 latent frames -> 81 frames), used for the depth and world-point outputs on the LAST denoising step only
-(SURVEY §8 a19).  Same state_dict keys; convolution / interpolation work stays on torch (cuDNN / ATen) in this round,
+(SURVEY §8 a19).  Same state_dict keys; stage 1 (LayerNorm + 1x1 projections of the 2048-wide tokens) runs on the fwb200 kernels, the spatial
+convolution / interpolation work stays on torch (cuDNN / ATen),
 frame chunking (4 / 16) and every index selection follow the reference so the outputs line up element for element.
 """
 from __future__ import annotations
@@ -93,6 +94,23 @@ def _make_scratch(in_shape: List[int], out_shape: int, groups: int = 1, expand: 
     return scratch
 
 
+class TokenLayerNorm(nn.LayerNorm):
+    """nn.LayerNorm over the 2048-wide aggregated tokens (same parameters and state_dict keys).  On a CUDA tensor the fwb200 row
+    kernel computes it (fp32 statistics, affine) and returns bf16 — under the reference's autocast the fp32 LayerNorm output is
+    cast to bf16 by the convolution that consumes it, so the values entering the projection are the same."""
+
+    def forward(self, x):
+        if not x.is_cuda:
+            return super().forward(x)
+        from fwb200 import engine as E
+        from fwb200 import ops
+        rows = x.reshape(-1, x.shape[-1])
+        if rows.dtype not in (torch.float32, torch.bfloat16):
+            rows = rows.float()
+        y = ops.ln_modulate(rows.contiguous(), eps=self.eps, w=E.f32(self, "w", self.weight), b=E.f32(self, "b", self.bias))
+        return y.view(*x.shape)
+
+
 class DPTHead_3D_Causal(nn.Module):
     """ref: dpt_head.py:13-320."""
 
@@ -104,7 +122,7 @@ class DPTHead_3D_Causal(nn.Module):
         self.patch_size, self.activation, self.conf_activation = patch_size, activation, conf_activation
         self.pos_embed, self.feature_only, self.down_ratio = pos_embed, feature_only, down_ratio
         self.intermediate_layer_idx, self.temporal_scale = intermediate_layer_idx, temporal_scale
-        self.norm = nn.LayerNorm(dim_in)
+        self.norm = TokenLayerNorm(dim_in)
         self.projects = nn.ModuleList([nn.Conv2d(dim_in, oc, kernel_size=1) for oc in out_channels])
         self.resize_layers = nn.ModuleList([
             nn.ConvTranspose2d(out_channels[0], out_channels[0], kernel_size=4, stride=4, padding=0),
@@ -143,9 +161,17 @@ class DPTHead_3D_Causal(nn.Module):
         feats = []
         for level, layer_idx in enumerate(self.intermediate_layer_idx):
             x = tokens_list[layer_idx][:, f0:f1, patch_start_idx:]
-            x = self.norm(x.reshape(B * S, -1, x.shape[-1]))
-            x = x.permute(0, 2, 1).reshape(B * S, x.shape[-1], gh, gw)
-            x = self.projects[level](x)
+            x = self.norm(x.reshape(B * S, -1, x.shape[-1]))          # CUDA: fwb_ln_modulate, bf16 out (see TokenLayerNorm)
+            if x.is_cuda:
+                # the 1x1 projection as a tcgen05 GEMM over tokens [S*gh*gw, 2048] x [oc, 2048]^T, conv output rounded
+                # to bf16 as under autocast; the token-major result is re-laid as NCHW for the convolutions behind it
+                from fwb200 import engine as E
+                from fwb200 import ops
+                y = E.lin(E.as_bf16(x).reshape(-1, x.shape[-1]), self.projects[level], round_flags=ops.ROUND_AFTER_BIAS)
+                x = y.view(B * S, gh, gw, -1).permute(0, 3, 1, 2).contiguous()
+            else:   # CPU: plain torch, only used by the index / golden unit tests of the host logic
+                x = x.permute(0, 2, 1).reshape(B * S, x.shape[-1], gh, gw)
+                x = self.projects[level](x)
             if self.pos_embed:
                 x = self._apply_pos_embed(x, W, H)
             feats.append(self.resize_layers[level](x))
