@@ -674,6 +674,12 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
+        try:                                    # tidy NCCL shutdown (no "destroy_process_group() was not called" warnings)
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.destroy_process_group()
+        except Exception:
+            pass
 
 
 if __name__ == "__main__":
