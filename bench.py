@@ -448,11 +448,15 @@ def run_ours(args):
     fwb200.prof_enable(prefixes=[dom_tag] if not args.breakdown else None)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.profiler_range:
+        torch.cuda.profiler.start()             # ncu --profile-from-start off: capture exactly the timed steps
     e0.record()
     for i in range(args.steps):
         lat = one_step(lat, args.warmup + i)
     e1.record()
     barrier()
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     launches = fwb200.launch_count()
     prof = fwb200.prof_disable()
     ms = e0.elapsed_time(e1)
@@ -657,6 +661,8 @@ def main():
     ap.add_argument("--irg", type=int, default=24)
     ap.add_argument("--breakdown", action="store_true", help="time every fwb200 launch with CUDA events and add a per-kernel table")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed steps (for `ncu --profile-from-start off`; never a bench value)")
     ap.add_argument("--parallel", default="auto", choices=["auto", "cfg", "sp"],
                     help="N > 1: cfg = CFG-parallel x sequence-parallel halves (default for even N), sp = sequence parallel over all ranks")
     ap.add_argument("--gpu-reference", default="auto", choices=["auto", "off"],
