@@ -44,3 +44,5 @@ for i,n in enumerate(h):
     if any(w in n for w in ['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','launch__registers_per_thread','sm__cycles_elapsed.avg.per_second']) or ('tensor' in n and 'pct' in n): print(n, '=', v[i])
 " | head -20
 ls -la gpurun_out/*.ncu-rep
+# reduced-size smoke of the wan22 workload (two experts, expert switch inside the window) before the 8-GPU run
+timeout 600 python bench.py --workload wan22_720p --frames 5 --h 16 --w 24 --pcb 2 --irg 2 --steps 2 --warmup 1 --no-cpu-baseline --gpu-reference off > gpurun_out/r02_bench_wan22_reduced.json 2> gpurun_out/r02_bench_wan22_reduced.err; head -c 1200 gpurun_out/r02_bench_wan22_reduced.json; tail -4 gpurun_out/r02_bench_wan22_reduced.err
