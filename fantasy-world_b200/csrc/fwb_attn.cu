@@ -41,6 +41,7 @@ struct AttnParams {
   __nv_bfloat16* out;
   long long o_sb, o_sl, o_sh;
   int Lq, Lk, d_real;
+  int pv_n;          // N of the PV MMAs: head_dim of the kernel instance, or 96 for head_dim 96 on the 128 instance (native width)
   float scale_log2;
   int accumulate;  // out = bf16(out + bf16(result))  (sum of two attentions sharing q: wan_video_dit.py:197-200)
   // split-KV mode (sequence parallel pipelining): write the subset-normalised result in fp32 and the row log-sum-exp
@@ -265,7 +266,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ------------------------------------ MMA issuer --------------------------------------
     if (elect_one()) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);  // B = V is MN-major (d contiguous)
+      const uint32_t idesc_pv = make_idesc_bf16(BQ, p.pv_n, 0, 1);  // B = V is MN-major (d contiguous); N = 96 skips the zero-padded columns
       const int ksteps_qk = (p.d_real + 15) / 16;
       const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
 
@@ -682,7 +683,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     if (elect_one()) {
       const int i = warp - 8;
       constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BK, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, D, 0, 1);  // B = V is MN-major (d contiguous)
+      const uint32_t idesc_pv = make_idesc_bf16(BQ, p.pv_n, 0, 1);  // B = V is MN-major (d contiguous)
       const int ksteps_qk = (p.d_real + 15) / 16;
       const uint32_t qa = smem_u32(sQ) + i * Cfg::kQTileBytes, k_addr = smem_u32(sK), v_addr = smem_u32(sV);
       const uint32_t s_tmem = tmem_base + Cfg::kColS + i * Cfg::kTileCols;
@@ -967,7 +968,8 @@ __global__ void attn_merge_kernel(const float* __restrict__ part, const float* _
 // (DESIGN.md), so this is not per-stream state.
 int g_attn_variant = 0;     // 0: per head_dim default (64 -> decoupled attn2, 96 / 128 -> v1: measured), 1: v1, 2: decoupled attn2
 int g_attn_tail_split = 1;  // key-split tail of the tile schedule on / off
-int g_attn_poly = -1;       // -1: per head_dim default, else 0 / 2 / 3 / 4 = pairs out of 8 on the exp2 polynomial
+int g_attn_poly = -1;       // -1: per head_dim default, else 0 / 2 = pairs out of 8 on the exp2 polynomial
+int g_attn_pv96 = 0;        // head_dim 96: PV MMAs with N = 96 instead of the zero-padded 128 (fwb_attn_set_pv_n96)
 
 // exp2 polynomial share per head_dim (pairs of 8); set from the A/B measurements in profiles/r02_attention.md
 inline int default_poly(int D) { (void)D; return 2; }   // 2 of 8 pairs: +1 % (head_dim 128), +13 % (96), +10 % (64), r02_attn_sweep.log
@@ -1034,6 +1036,11 @@ extern "C" int fwb_attn_set_tail_split(int enabled) {
 extern "C" int fwb_attn_set_exp2_poly(int pairs_of_8) {
   FWB_CHECK(pairs_of_8 == -1 || pairs_of_8 == 0 || pairs_of_8 == 2, "attn_set_exp2_poly: -1 (default), 0 or 2 pairs out of every 8");
   g_attn_poly = pairs_of_8;
+  return FWB_OK;
+}
+
+extern "C" int fwb_attn_set_pv_n96(int enabled) {
+  g_attn_pv96 = enabled ? 1 : 0;
   return FWB_OK;
 }
 
@@ -1110,6 +1117,7 @@ static int attn_impl(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_t
   p.out = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(out->ptr));
   p.o_sb = out->sb; p.o_sl = out->sl; p.o_sh = out->sh;
   p.Lq = Lq; p.Lk = Lk; p.d_real = D;
+  p.pv_n = (D == 96) ? (g_attn_pv96 ? 96 : 128) : D;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.accumulate = accumulate;
   p.part_out = part_out;

@@ -20,6 +20,7 @@ struct BringupParams {
   uint32_t b_lbo, b_sbo, b_kadv;  // bytes
   uint32_t b_box_stride;          // bytes between consecutive TMA boxes of B in smem
   uint32_t a_tmem_kadv;           // TMEM columns per K=16 step when A is in TMEM
+  int mma_n;                      // N of the MMA instruction (<= N; N = width of the loaded B / read-back D)
 };
 
 __global__ void __launch_bounds__(128, 1)
@@ -86,7 +87,7 @@ bringup_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (threadIdx.x == 0) {
     mbar_wait(&bar_load, 0);
     tc_fence_after();
-    const uint32_t idesc = make_idesc_bf16(128, N, 0, p.b_mn_major ? 1 : 0);
+    const uint32_t idesc = make_idesc_bf16(128, p.mma_n, 0, p.b_mn_major ? 1 : 0);
     for (int kk = 0; kk < K / 16; ++kk) {
       uint64_t bdesc;
       if (!p.b_mn_major) {
@@ -124,8 +125,23 @@ bringup_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+static int bringup_impl(const void* A, const void* B, float* D, int N, int K, int a_in_tmem, int b_mn_major, const uint32_t* overrides,
+                        int mma_n, cudaStream_t stream);
+
 extern "C" int fwb_bringup_mma(const void* A, const void* B, float* D, int N, int K, int a_in_tmem, int b_mn_major,
                                const uint32_t* overrides /* 8 values or NULL */, cudaStream_t stream) {
+  return bringup_impl(A, B, D, N, K, a_in_tmem, b_mn_major, overrides, N, stream);
+}
+
+// The PV configuration of the attention (A = P in TMEM, B = V MN-major in two 64-column SWIZZLE_128B boxes) with an MMA N that is
+// narrower than the loaded tile: mma_n = 96 on a 128-wide V tile is the native head_dim-96 PV (columns [0, mma_n) of D are defined).
+extern "C" int fwb_bringup_mma_pv_n(const void* A, const void* B, float* D, int N, int K, int mma_n, cudaStream_t stream) {
+  FWB_CHECK(mma_n > 0 && mma_n <= N && mma_n % 16 == 0, "bringup: mma_n must be a multiple of 16 and <= N");
+  return bringup_impl(A, B, D, N, K, 1, 1, nullptr, mma_n, stream);
+}
+
+static int bringup_impl(const void* A, const void* B, float* D, int N, int K, int a_in_tmem, int b_mn_major, const uint32_t* overrides,
+                        int mma_n, cudaStream_t stream) {
   FWB_CHECK(N == 64 || N == 128 || N == 256, "bringup: N must be 64/128/256");
   FWB_CHECK(K % 64 == 0 && K >= 64 && K <= 256, "bringup: K must be a multiple of 64 in [64,256]");
   BringupParams p;
@@ -148,6 +164,7 @@ extern "C" int fwb_bringup_mma(const void* A, const void* B, float* D, int N, in
     p.b_kadv = 16 * 128;        // 16 k-rows per MMA
   }
   p.a_tmem_kadv = 8;
+  p.mma_n = mma_n;
   if (overrides) {
     if (overrides[0] != 0xFFFFFFFFu) p.a_lbo = overrides[0];
     if (overrides[1] != 0xFFFFFFFFu) p.a_sbo = overrides[1];

@@ -54,10 +54,12 @@ def _load():
     lib.fwb_attn_set_tail_split.argtypes = [i32]
     lib.fwb_attn_set_exp2_poly.argtypes = [i32]
     lib.fwb_attn_set_mufu_pingpong.argtypes = [i32, i32]
+    lib.fwb_attn_set_pv_n96.argtypes = [i32]
     lib.fwb_attn_fwd.argtypes = [C.POINTER(Tensor4)] * 4 + [i32, i32, i32, i32, i32, f32, i32, vp, C.c_size_t, vp]
     lib.fwb_attn_fwd_partial.argtypes = [C.POINTER(Tensor4)] * 3 + [vp, vp, i32, i32, i32, i32, i32, f32, vp, C.c_size_t, vp]
     lib.fwb_attn_merge.argtypes = [vp, vp, C.POINTER(Tensor4), i32, i32, i32, i32, i32, vp]
     lib.fwb_bringup_mma.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.fwb_bringup_mma_pv_n.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.fwb_ln_modulate.argtypes = [vp, i32, i64, i32, i32, f32, vp, vp, vp, vp, vp, i64, vp]
     lib.fwb_rmsnorm_rope.argtypes = [vp, i64, i32, i32, vp, f32, vp, i32, vp]
     lib.fwb_ln64_rope2d.argtypes = [vp, i64, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp]

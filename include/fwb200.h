@@ -127,6 +127,8 @@ int fwb_attn_set_variant(int variant);
 int fwb_attn_set_tail_split(int enabled);
 int fwb_attn_set_exp2_poly(int pairs_of_8);
 int fwb_attn_set_mufu_pingpong(int kernel, int enabled);
+/* head_dim 96 (runs on the 128-wide instance with zero-filled columns): issue the PV MMAs with N = 96 instead of 128 (0 = off) */
+int fwb_attn_set_pv_n96(int enabled);
 
 /* ---- K7: LayerNorm (+affine) (+modulate) -> bf16 ------------------------------------------------------------------
  * out[r,:] = bf16( (LN(x[r,:]) * w + b) * mul + add ), any of (w,b), mul, add may be NULL.  fp32 statistics.
@@ -160,6 +162,8 @@ int fwb_cfg_euler_step(void* latents, const void* pred_pos, const void* pred_neg
 /* ---- bring-up micro-test (tests only; pins tcgen05 descriptor encodings on hardware) ------------------------------ */
 int fwb_bringup_mma(const void* A, const void* B, float* D, int N, int K, int a_in_tmem, int b_mn_major,
                     const uint32_t* overrides, fwb_stream_t stream);
+/* PV configuration (A in TMEM, B MN-major) with an MMA N narrower than the loaded tile (mma_n = 96: native head_dim-96 PV). */
+int fwb_bringup_mma_pv_n(const void* A, const void* B, float* D, int N, int K, int mma_n, fwb_stream_t stream);
 
 #ifdef __cplusplus
 }

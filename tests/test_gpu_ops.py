@@ -347,3 +347,40 @@ def test_cfg_euler_step(fwb):
     ref = ref + pred * torch.tensor(-0.0123)
     fwb.cfg_euler_step_(lat, p, q, 5.0, -0.0123)
     torch.testing.assert_close(lat.float(), ref.float(), rtol=8e-3, atol=8e-3)
+
+
+@pytest.mark.parametrize("mma_n", [128, 96, 64])
+def test_bringup_pv_mma_narrower_than_the_v_tile(fwb, mma_n):
+    """tcgen05.mma in the attention's PV configuration (A = P from TMEM, B = V MN-major in two 64-column SWIZZLE_128B boxes) with an
+    instruction N narrower than the loaded tile: the first mma_n columns of D must be exact.  N = 96 is the native head_dim-96 PV."""
+    import ctypes as C
+    torch.manual_seed(3)
+    K, N = 128, 128
+    A = _bf(torch.randn(128, K, device="cuda"))
+    B = _bf(torch.randn(K, N, device="cuda"))             # [K][N]: MN-major operand, N contiguous
+    D = torch.zeros(128, N, device="cuda", dtype=torch.float32)
+    rc = fwb.lib.fwb_bringup_mma_pv_n(A.data_ptr(), B.data_ptr(), D.data_ptr(), N, K, mma_n, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, fwb.lib.fwb_last_error()
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float()
+    torch.testing.assert_close(D[:, :mma_n], ref[:, :mma_n], rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_attention_head_dim_96_native_pv_width(fwb, variant):
+    """fwb_attn_set_pv_n96: head_dim 96 with PV MMAs of N = 96 (no work on the zero-padded columns) == the padded N = 128 result."""
+    torch.manual_seed(9)
+    B, H, Lq, Lk, D = 1, 12, 1560, 1565, 96
+    q, k, v = (_bf(torch.randn(B, L, H, D, device="cuda")) for L in (Lq, Lk, Lk))
+    try:
+        fwb.lib.fwb_attn_set_variant(variant)
+        fwb.lib.fwb_attn_set_pv_n96(0)
+        ref = fwb.attention(q, k, v)
+        fwb.lib.fwb_attn_set_pv_n96(1)
+        out = fwb.attention(q, k, v)
+        torch.cuda.synchronize()
+    finally:
+        fwb.lib.fwb_attn_set_pv_n96(0)
+        fwb.lib.fwb_attn_set_variant(0)
+    assert torch.equal(out, ref)
+    torch.testing.assert_close(out.float(), _attn_ref(q, k, v), rtol=2e-2, atol=6e-3)

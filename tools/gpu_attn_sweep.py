@@ -56,6 +56,16 @@ for (B, H, Lq, Lk, D, name) in SHAPES:
             if var in (1, 2):
                 lib.fwb_attn_set_mufu_pingpong(var, pp)
             res[c].append(fl / timeit(lambda: fwb200.attention(q, k, v, out=o)) / 1e9)
+    if D == 96:     # native PV width A/B on the default kernel
+        lib.fwb_attn_set_variant(0)
+        lib.fwb_attn_set_exp2_poly(-1)
+        ab = {0: [], 1: []}
+        for rnd in range(3):
+            for on in (0, 1):
+                lib.fwb_attn_set_pv_n96(on)
+                ab[on].append(fl / timeit(lambda: fwb200.attention(q, k, v, out=o)) / 1e9)
+        lib.fwb_attn_set_pv_n96(0)
+        emit("   head_dim 96 PV N=128: " + "/".join(f"{x:.0f}" for x in ab[0]) + "   PV N=96: " + "/".join(f"{x:.0f}" for x in ab[1]) + " TF")
     lib.fwb_attn_set_variant(0)
     lib.fwb_attn_set_exp2_poly(-1)
     lib.fwb_attn_set_mufu_pingpong(1, 0)
