@@ -178,13 +178,23 @@ def _t4(t: torch.Tensor) -> Tensor4:
 _attn_ws: dict = {}
 
 
+_ATTN_WS_MAX = 8
+
+
 def _attn_workspace(device):
-    """Scratch for the tail split of the attention tile schedule (fwb_attn_workspace_bytes, ~20 MB), one per (device, stream)."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    ws = _attn_ws.get(key)
+    """Scratch for the tail split of the attention tile schedule (fwb_attn_workspace_bytes, ~78 MB), one per (device, stream).
+    Stream handles are recycled by the driver and a process may create many side streams, so the cache is bounded: beyond
+    _ATTN_WS_MAX entries the least recently used one is dropped (its memory returns to the caching allocator once the kernels
+    already queued on it have run: the allocator keeps a block alive until its recorded stream uses are complete)."""
+    stream = torch.cuda.current_stream(device)
+    key = (device.index, stream.cuda_stream)
+    ws = _attn_ws.pop(key, None)
     if ws is None:
         ws = torch.empty(int(lib.fwb_attn_workspace_bytes()), device=device, dtype=torch.uint8)
-        _attn_ws[key] = ws
+        while len(_attn_ws) >= _ATTN_WS_MAX:
+            old = _attn_ws.pop(next(iter(_attn_ws)))
+            old.record_stream(stream)
+    _attn_ws[key] = ws          # re-insert: dict order = recency
     return ws
 
 
