@@ -969,7 +969,8 @@ __global__ void attn_merge_kernel(const float* __restrict__ part, const float* _
 int g_attn_variant = 0;     // 0: per head_dim default (64 -> decoupled attn2, 96 / 128 -> v1: measured), 1: v1, 2: decoupled attn2
 int g_attn_tail_split = 1;  // key-split tail of the tile schedule on / off
 int g_attn_poly = -1;       // -1: per head_dim default, else 0 / 2 = pairs out of 8 on the exp2 polynomial
-int g_attn_pv96 = 0;        // head_dim 96: PV MMAs with N = 96 instead of the zero-padded 128 (fwb_attn_set_pv_n96)
+int g_attn_pv96 = 1;        // head_dim 96: PV MMAs with N = 96 instead of the zero-padded 128 (fwb_attn_set_pv_n96): bit-identical,
+                            // +2.4 % on the adapter shapes (profiles/r02_attention.md)
 
 // exp2 polynomial share per head_dim (pairs of 8); set from the A/B measurements in profiles/r02_attention.md
 inline int default_poly(int D) { (void)D; return 2; }   // 2 of 8 pairs: +1 % (head_dim 128), +13 % (96), +10 % (64), r02_attn_sweep.log

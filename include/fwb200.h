@@ -127,7 +127,8 @@ int fwb_attn_set_variant(int variant);
 int fwb_attn_set_tail_split(int enabled);
 int fwb_attn_set_exp2_poly(int pairs_of_8);
 int fwb_attn_set_mufu_pingpong(int kernel, int enabled);
-/* head_dim 96 (runs on the 128-wide instance with zero-filled columns): issue the PV MMAs with N = 96 instead of 128 (0 = off) */
+/* head_dim 96 (runs on the 128-wide instance with zero-filled columns): issue the PV MMAs with N = 96 instead of 128
+ * (default on: bit-identical result, no MMA work on the padded columns; 0 = off for the A/B) */
 int fwb_attn_set_pv_n96(int enabled);
 
 /* ---- K7: LayerNorm (+affine) (+modulate) -> bf16 ------------------------------------------------------------------

@@ -380,7 +380,7 @@ def test_attention_head_dim_96_native_pv_width(fwb, variant):
         out = fwb.attention(q, k, v)
         torch.cuda.synchronize()
     finally:
-        fwb.lib.fwb_attn_set_pv_n96(0)
+        fwb.lib.fwb_attn_set_pv_n96(1)          # the default
         fwb.lib.fwb_attn_set_variant(0)
     assert torch.equal(out, ref)
     torch.testing.assert_close(out.float(), _attn_ref(q, k, v), rtol=2e-2, atol=6e-3)

@@ -64,7 +64,7 @@ for (B, H, Lq, Lk, D, name) in SHAPES:
             for on in (0, 1):
                 lib.fwb_attn_set_pv_n96(on)
                 ab[on].append(fl / timeit(lambda: fwb200.attention(q, k, v, out=o)) / 1e9)
-        lib.fwb_attn_set_pv_n96(0)
+        lib.fwb_attn_set_pv_n96(1)
         emit("   head_dim 96 PV N=128: " + "/".join(f"{x:.0f}" for x in ab[0]) + "   PV N=96: " + "/".join(f"{x:.0f}" for x in ab[1]) + " TF")
     lib.fwb_attn_set_variant(0)
     lib.fwb_attn_set_exp2_poly(-1)
