@@ -353,9 +353,11 @@ def gpu_reference_step(f, h, w, n_pcb, n_irg):
     if not ((ROOT / "oracle" / "_ref" / "FantasyWorld").exists() or Path("/root/reference/FantasyWorld").exists()):
         return {"unavailable": "reference not staged (python oracle/make_ref.py)"}
     out = _subprocess_json([sys.executable, str(ROOT / "oracle" / "ref_runner.py"), "step", "--device", "cuda", "--grid", str(f), str(h), str(w),
-                            "--pcb", str(n_pcb), "--irg", str(n_irg), "--steps", "1", "--warmup", "1", "--modes", "bf16_fa2"], timeout=900)
+                            "--pcb", str(n_pcb), "--irg", str(n_irg), "--steps", "1", "--warmup", "1", "--modes", "bf16_fa2,bf16_sdpa"], timeout=1200)
     if "ms_per_step" in out:
-        out["steps_per_s"] = 1e3 / out["ms_per_step"]
+        out["steps_per_s"] = 1e3 / out["ms_per_step"]          # the reference's default path on this box (flash-attn for the DiT)
+        for m in out.get("modes", {}).values():
+            m["steps_per_s"] = 1e3 / m["ms_per_step"]
         out["what"] = "unmodified reference (oracle/_ref), model.to(bf16) + torch.autocast(cuda, bf16), same synthetic shapes, same GPU"
     return out
 
@@ -491,6 +493,11 @@ def run_ours(args):
         t = torch.tensor([ms_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t)
+        # all measurements are in: tear the NCCL groups down TOGETHER (rank 0 goes on alone to the CPU / reference legs, which take
+        # minutes; a late one-sided destroy against peers that have already exited is what must not happen)
+        dist.barrier()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
 
     if rank != 0:
         return
@@ -680,12 +687,6 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
-        try:                                    # tidy NCCL shutdown (no "destroy_process_group() was not called" warnings)
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized():
-                dist.destroy_process_group()
-        except Exception:
-            pass
 
 
 if __name__ == "__main__":

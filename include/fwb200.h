@@ -139,7 +139,8 @@ int fwb_attn_set_pv_n96(int enabled);
  * x: [rows,C] bf16 or fp32 (x_dtype), C % 8 == 0, C <= 5120; vectors fp32 [C]; out bf16 [rows,C]. */
 int fwb_ln_modulate(const void* x, int x_dtype, int64_t ldx, int rows, int C, float eps, const float* w, const float* b,
                     const float* mul, const float* add, void* out, int64_t ldo, fwb_stream_t stream);
-/* Tuning hook: resident 128-thread CTAs per SM of the persistent row kernels (fwb_ln_modulate, fwb_rmsnorm_rope); 1..16, default 8 */
+/* Tuning hook: 128-thread CTAs per SM of the persistent row kernels (fwb_ln_modulate, fwb_rmsnorm_rope): 0 = one full wave of as many
+ * as fit (occupancy query per kernel, default), 1..16 = forced (A/B measurements) */
 int fwb_rowwise_set_ctas_per_sm(int n);
 
 /* ---- K8+K9 (DiT / adapter): full-channel RMSNorm then interleaved-pair RoPE, in place --------------------------------

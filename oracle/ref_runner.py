@@ -239,39 +239,46 @@ def cmd_joint(a):
 
 
 def cmd_step(a):
-    """K denoise steps through the reference's own joint_forward + scheduler (loop body of model_wan21.py:289-322)."""
+    """K denoise steps through the reference's own joint_forward + scheduler (loop body of model_wan21.py:289-322), once per
+    requested mode (the model is built once; e.g. bf16_fa2 then bf16_sdpa = both FLASH_ATTN_2_AVAILABLE settings)."""
     f, h, w = a.grid
     model, ns = build(a.pcb + a.irg, a.pcb, False, a.device)
-    mode = a.modes[0]
     lens = torch.ones(f, dtype=torch.long, device=a.device)
     lens[1:] = 4
     sched = model.pipe.scheduler
     sched.set_timesteps(50)
-    with mode_ctx(model, ns, mode, a.device) as dt:
-        d = joint_inputs(f, h, w, a.text_len, a.device, dt)
-        lat = d["latents"].clone()
-        kw = dict(clip_feature=d["clip_feature"], y=d["y"], use_gradient_checkpointing=False, plucker_fea=d["plucker_fea"],
-                  plucker_context_lens=lens)
+    runs = {}
+    for mode in a.modes:
+        with mode_ctx(model, ns, mode, a.device) as dt:
+            d = joint_inputs(f, h, w, a.text_len, a.device, dt)
+            lat = d["latents"].clone()
+            kw = dict(clip_feature=d["clip_feature"], y=d["y"], use_gradient_checkpointing=False, plucker_fea=d["plucker_fea"],
+                      plucker_context_lens=lens)
 
-        def one(i, lat):
-            t = sched.timesteps[i % len(sched.timesteps)].unsqueeze(0).to(dtype=dt, device=a.device)
-            pos, _ = model.joint_forward(lat, timestep=t, context=d["context_pos"], **kw)
-            neg, _ = model.joint_forward(lat, timestep=t, context=d["context_neg"], **kw)
-            pred = neg + 5.0 * (pos - neg)
-            return sched.step(pred, sched.timesteps[i % len(sched.timesteps)], lat)
+            def one(i, lat):
+                t = sched.timesteps[i % len(sched.timesteps)].unsqueeze(0).to(dtype=dt, device=a.device)
+                pos, _ = model.joint_forward(lat, timestep=t, context=d["context_pos"], **kw)
+                neg, _ = model.joint_forward(lat, timestep=t, context=d["context_neg"], **kw)
+                pred = neg + 5.0 * (pos - neg)
+                return sched.step(pred, sched.timesteps[i % len(sched.timesteps)], lat)
 
-        for i in range(a.warmup):
-            lat = one(i, lat)
-        _sync(a.device)
-        ms = []
-        for i in range(a.steps):
-            (lat), m = timed(lambda: one(a.warmup + i, lat), a.device, 1)
-            ms.append(m[0])
-        backend = "flash_attn_func" if ns.dit.FLASH_ATTN_2_AVAILABLE else "F.scaled_dot_product_attention"
+            for i in range(a.warmup):
+                lat = one(i, lat)
+            _sync(a.device)
+            ms = []
+            for i in range(a.steps):
+                (lat), m = timed(lambda: one(a.warmup + i, lat), a.device, 1)
+                ms.append(m[0])
+            backend = "flash_attn_func" if ns.dit.FLASH_ATTN_2_AVAILABLE else "F.scaled_dot_product_attention"
+        runs[mode] = {"ms_per_step": sum(ms) / len(ms), "ms_each": ms, "dit_attention_backend": backend,
+                      "finite": bool(torch.isfinite(lat.float()).all())}
+        del d, lat
     mem = torch.cuda.max_memory_allocated() / 2**30 if torch.device(a.device).type == "cuda" else None
-    print(json.dumps({"cmd": "step", "grid": [f, h, w], "pcb": a.pcb, "irg": a.irg, "mode": mode, "device": a.device, "steps": a.steps,
-                      "warmup": a.warmup, "ms_per_step": sum(ms) / len(ms), "ms_each": ms, "dit_attention_backend": backend,
-                      "max_mem_gib": mem, "threads": torch.get_num_threads(), "finite": bool(torch.isfinite(lat.float()).all())}))
+    first = runs[a.modes[0]]
+    print(json.dumps({"cmd": "step", "grid": [f, h, w], "pcb": a.pcb, "irg": a.irg, "mode": a.modes[0], "device": a.device, "steps": a.steps,
+                      "warmup": a.warmup, "ms_per_step": first["ms_per_step"], "ms_each": first["ms_each"],
+                      "dit_attention_backend": first["dit_attention_backend"], "finite": first["finite"], "modes": runs,
+                      "max_mem_gib": mem, "threads": torch.get_num_threads()}))
 
 
 def cmd_schema(a):
