@@ -174,11 +174,16 @@ __device__ __forceinline__ float softmax_exp(const uint32_t (&v)[N], float sl2, 
   return s0 + s1;
 }
 
-template <int D, int POLY>
-__global__ void __launch_bounds__(kAttnThreads, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+// MC (multicast pairs): the kernel runs as clusters of two CTAs that work on adjacent 256-row query blocks of the SAME (batch, head).
+// They walk the K/V tiles in lock-step and share every tile: each CTA issues the TMA load of ONE of the tile's two 64-column boxes
+// with `.multicast::cluster`, so a K/V tile crosses the L2 -> SM fabric once per pair instead of once per CTA (the kernel re-reads
+// every K/V tile from L2 for each of the 128 query blocks of a head: 86 GB per DiT self-attention, profiles/r02_attn_d128.md), and a
+// stage is refilled only when both CTAs' MMAs have released it (empty barriers count 2, commits multicast to both CTAs).
+template <int D, int POLY, bool MC>
+__device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p) {
   using Cfg = AttnCfg<D>;
+  static_assert(!MC || Cfg::kBoxes == 2, "multicast pairs: one 64-column box per CTA (head_dim 128 instance)");
+  const uint32_t crank = MC ? cluster_ctarank() : 0;
   constexpr int ST = Cfg::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -223,9 +228,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     for (int s = 0; s < ST; ++s) {
       mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
+      mbar_init(&k_empty[s], MC ? 2 : 1);   // MC: released by the MMA threads of both CTAs of the pair
       mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
+      mbar_init(&v_empty[s], MC ? 2 : 1);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmQ);
@@ -239,6 +244,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if constexpr (MC) cluster_sync_all();   // the peer's barriers exist before any multicast load / commit targets them
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 9) {
@@ -254,12 +260,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t s = j % ST, ph = (j / ST) & 1;
         mbar_wait(&k_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&k_full[s], Cfg::kTileBytes);
-        for (int b = 0; b < Cfg::kBoxes; ++b)
-          tma_load_4d(sK + s * Cfg::kTileBytes + b * 16384, &tmK, &k_full[s], b * 64, head, (kv0 + j) * BKV, batch);
+        if constexpr (MC) {   // this CTA's box for both CTAs; the other box arrives from the peer (it may land before the expect_tx above)
+          tma_load_4d_mc(sK + s * Cfg::kTileBytes + crank * 16384, &tmK, &k_full[s], crank * 64, head, (kv0 + j) * BKV, batch, 3);
+        } else {
+          for (int b = 0; b < Cfg::kBoxes; ++b)
+            tma_load_4d(sK + s * Cfg::kTileBytes + b * 16384, &tmK, &k_full[s], b * 64, head, (kv0 + j) * BKV, batch);
+        }
         mbar_wait(&v_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[s], Cfg::kTileBytes);
-        for (int b = 0; b < Cfg::kBoxes; ++b)
-          tma_load_4d(sV + s * Cfg::kTileBytes + b * 16384, &tmV, &v_full[s], b * 64, head, (kv0 + j) * BKV, batch);
+        if constexpr (MC) {
+          tma_load_4d_mc(sV + s * Cfg::kTileBytes + crank * 16384, &tmV, &v_full[s], crank * 64, head, (kv0 + j) * BKV, batch, 3);
+        } else {
+          for (int b = 0; b < Cfg::kBoxes; ++b)
+            tma_load_4d(sV + s * Cfg::kTileBytes + b * 16384, &tmV, &v_full[s], b * 64, head, (kv0 + j) * BKV, batch);
+        }
       }
     }
   } else if (warp == 8) {
@@ -291,6 +305,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       };
 
+      auto release = [&](uint64_t* bar) {   // K / V stage consumed: tell the producer(s) that fill it
+        if constexpr (MC) tc_commit_mc(bar, 3);
+        else tc_commit(bar);
+      };
       mbar_wait(&q_full[0], 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
@@ -300,7 +318,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_after();
       issue_qk(1, 0);
       tc_commit(&s_full[1]);
-      tc_commit(&k_empty[0]);
+      release(&k_empty[0]);
 
       for (int j = 0; j < n_kv; ++j) {
         const uint32_t vs = j % ST, vph = (j / ST) & 1;
@@ -311,7 +329,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (i == 0) mbar_wait(&v_full[vs], vph);
           tc_fence_after();
           issue_pv(i, vs, j > 0);
-          if (i == 1) tc_commit(&v_empty[vs]);
+          if (i == 1) release(&v_empty[vs]);
           if (j + 1 < n_kv) {
             const uint32_t ks = (j + 1) % ST, kph = ((j + 1) / ST) & 1;
             if (i == 0) {
@@ -320,7 +338,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             issue_qk(i, ks);  // overwrites S_i/P_i: ordered after PV_i(j) by in-order MMA execution
             tc_commit(&s_full[i]);
-            if (i == 1) tc_commit(&k_empty[ks]);
+            if (i == 1) release(&k_empty[ks]);
           } else {
             tc_commit(&o_full[i]);
           }
@@ -484,7 +502,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();   // neither CTA may exit while the peer can still multicast into it or arrive on its barriers
   if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+template <int D, int POLY>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  attn_fwd_body<D, POLY, false>(tmQ, tmK, tmV, p);
+}
+
+template <int D, int POLY>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAttnThreads, 1)
+attn_fwd_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  attn_fwd_body<D, POLY, true>(tmQ, tmK, tmV, p);
 }
 
 int make_qkv_map(CUtensorMap* m, const fwb_tensor4_t* t, int B, int H, int L, int D, int box_rows = 128) {
@@ -536,6 +569,8 @@ __global__ void attn_tail_merge_kernel(const AttnParams p, int tail) {
   }
 }
 
+int g_attn_multicast = 0;   // aliased kernel at head_dim 96 / 128: CTA pairs sharing K/V tiles by TMA multicast (fwb_attn_set_multicast)
+
 template <int D, int POLY>
 int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B, int H,
                 cudaStream_t stream) {
@@ -547,7 +582,18 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
   const long long tail = n_tiles - p.n_full;
   const long long grid = p.n_full + (p.S > 1 ? tail * p.S : tail);
   FWB_CHECK(grid < (1ll << 31), "attn: grid too large");
-  attn_fwd_kernel<D, POLY><<<(unsigned)grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  bool mc = false;
+  if constexpr (D == 128) {
+    // multicast pairs need: both CTAs of a pair on the same (batch, head) -> an even number of query blocks; no key-split tail
+    mc = g_attn_multicast && p.S == 1 && (p.nq % 2) == 0 && (grid % 2) == 0;
+    if (mc) {
+      static AttrOnce once_mc;
+      if (once_mc.need(current_device()))
+        FWB_CUDA(cudaFuncSetAttribute(attn_fwd_mc_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+      attn_fwd_mc_kernel<D, POLY><<<(unsigned)grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+    }
+  }
+  if (!mc) attn_fwd_kernel<D, POLY><<<(unsigned)grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
   FWB_CUDA(cudaGetLastError());
   if (p.S > 1) {
     const long long total = tail * (2 * BQ) * (p.d_real / 8);
@@ -1037,6 +1083,11 @@ extern "C" int fwb_attn_set_tail_split(int enabled) {
 extern "C" int fwb_attn_set_exp2_poly(int pairs_of_8) {
   FWB_CHECK(pairs_of_8 == -1 || pairs_of_8 == 0 || pairs_of_8 == 2, "attn_set_exp2_poly: -1 (default), 0 or 2 pairs out of every 8");
   g_attn_poly = pairs_of_8;
+  return FWB_OK;
+}
+
+extern "C" int fwb_attn_set_multicast(int enabled) {
+  g_attn_multicast = enabled ? 1 : 0;
   return FWB_OK;
 }
 

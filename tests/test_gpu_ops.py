@@ -384,3 +384,31 @@ def test_attention_head_dim_96_native_pv_width(fwb, variant):
         fwb.lib.fwb_attn_set_variant(0)
     assert torch.equal(out, ref)
     torch.testing.assert_close(out.float(), _attn_ref(q, k, v), rtol=2e-2, atol=6e-3)
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,D", [(1, 4, 1024, 777, 128), (1, 12, 2048, 1565, 96), (2, 3, 512, 3000, 128), (1, 40, 4096, 8190, 128)])
+def test_attention_multicast_pairs_bit_identical(fwb, B, H, Lq, Lk, D):
+    """fwb_attn_set_multicast: the aliased kernel as clusters of two CTAs (adjacent query blocks of one head) that share every K/V tile
+    through TMA multicast and release a stage only when both have consumed it.  Same arithmetic in the same order per CTA: the output must
+    equal the non-cluster kernel's bit for bit, in the bf16 and in the split-KV (fp32 partial + lse) modes."""
+    torch.manual_seed(Lq + Lk)
+    q, k, v = (_bf(torch.randn(B, L, H, D, device="cuda")) for L in (Lq, Lk, Lk))
+    part = torch.empty(2, B, Lq, H, D, device="cuda")
+    lse = torch.empty(2, B, H, Lq, device="cuda")
+    try:
+        fwb.lib.fwb_attn_set_variant(1)
+        fwb.lib.fwb_attn_set_tail_split(0)
+        fwb.lib.fwb_attn_set_multicast(0)
+        ref = fwb.attention(q, k, v)
+        fwb.attention_partial(q, k, v, part[0], lse[0])
+        fwb.lib.fwb_attn_set_multicast(1)
+        out = fwb.attention(q, k, v)
+        fwb.attention_partial(q, k, v, part[1], lse[1])
+        torch.cuda.synchronize()
+    finally:
+        fwb.lib.fwb_attn_set_multicast(0)
+        fwb.lib.fwb_attn_set_tail_split(1)
+        fwb.lib.fwb_attn_set_variant(0)
+    assert torch.equal(out, ref)
+    assert torch.equal(part[1], part[0]) and torch.equal(lse[1], lse[0])
+    torch.testing.assert_close(out.float(), _attn_ref(q, k, v), rtol=2e-2, atol=6e-3)

@@ -56,6 +56,16 @@ for (B, H, Lq, Lk, D, name) in SHAPES:
             if var in (1, 2):
                 lib.fwb_attn_set_mufu_pingpong(var, pp)
             res[c].append(fl / timeit(lambda: fwb200.attention(q, k, v, out=o)) / 1e9)
+    if D in (96, 128) and (Lq + 255) // 256 % 2 == 0:     # CTA pairs sharing K/V tiles by TMA multicast, A/B on the default kernel
+        lib.fwb_attn_set_variant(0)
+        lib.fwb_attn_set_exp2_poly(-1)
+        ab = {0: [], 1: []}
+        for rnd in range(4):
+            for on in (0, 1):
+                lib.fwb_attn_set_multicast(on)
+                ab[on].append(fl / timeit(lambda: fwb200.attention(q, k, v, out=o), iters=6) / 1e9)
+        lib.fwb_attn_set_multicast(0)
+        emit(f"   [{name}] multicast off: " + "/".join(f"{x:.0f}" for x in ab[0]) + "   on: " + "/".join(f"{x:.0f}" for x in ab[1]) + " TF")
     if D == 96:     # native PV width A/B on the default kernel
         lib.fwb_attn_set_variant(0)
         lib.fwb_attn_set_exp2_poly(-1)
