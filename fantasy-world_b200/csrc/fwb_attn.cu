@@ -585,7 +585,9 @@ int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
   bool mc = false;
   if constexpr (D == 128) {
     // multicast pairs need: both CTAs of a pair on the same (batch, head) -> an even number of query blocks; no key-split tail
-    mc = g_attn_multicast && p.S == 1 && (p.nq % 2) == 0 && (grid % 2) == 0;
+    // ... and it only pays on long key sequences at the full head_dim (measured: -9 % at 512 keys — the pair runs in lock-step —, -1 % at
+    // head_dim 96, +1 % isolated / see profiles/r02_attention.md for the in-step A/B at head_dim 128)
+    mc = g_attn_multicast && p.S == 1 && (p.nq % 2) == 0 && (grid % 2) == 0 && p.d_real == 128 && p.Lk >= 2048;
     if (mc) {
       static AttrOnce once_mc;
       if (once_mc.need(current_device()))
