@@ -569,7 +569,8 @@ __global__ void attn_tail_merge_kernel(const AttnParams p, int tail) {
   }
 }
 
-int g_attn_multicast = 0;   // aliased kernel at head_dim 96 / 128: CTA pairs sharing K/V tiles by TMA multicast (fwb_attn_set_multicast)
+int g_attn_multicast = 1;   // aliased kernel, head_dim 128, >= 2048 keys: CTA pairs sharing K/V tiles by TMA multicast (fwb_attn_set_multicast);
+                            // bit-identical, -1.0 % step time in the in-step A/B (profiles/r02_attention.md §7)
 
 template <int D, int POLY>
 int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B, int H,

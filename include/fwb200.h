@@ -130,8 +130,9 @@ int fwb_attn_set_mufu_pingpong(int kernel, int enabled);
 /* head_dim 96 (runs on the 128-wide instance with zero-filled columns): issue the PV MMAs with N = 96 instead of 128
  * (default on: bit-identical result, no MMA work on the padded columns; 0 = off for the A/B) */
 int fwb_attn_set_pv_n96(int enabled);
-/* aliased kernel, head_dim 96 / 128, even number of 256-row query blocks, no key-split tail: run as clusters of two CTAs on adjacent
- * query blocks of one head that share every K/V tile through TMA multicast (halves the L2 -> SM traffic); same results */
+/* aliased kernel, head_dim 128, >= 2048 keys, even number of 256-row query blocks, no key-split tail: run as clusters of two CTAs on
+ * adjacent query blocks of one head that share every K/V tile through TMA multicast (halves the L2 -> SM traffic); bit-identical
+ * results; default on (0 = off for the A/B) */
 int fwb_attn_set_multicast(int enabled);
 
 /* ---- K7: LayerNorm (+affine) (+modulate) -> bf16 ------------------------------------------------------------------

@@ -406,7 +406,7 @@ def test_attention_multicast_pairs_bit_identical(fwb, B, H, Lq, Lk, D):
         fwb.attention_partial(q, k, v, part[1], lse[1])
         torch.cuda.synchronize()
     finally:
-        fwb.lib.fwb_attn_set_multicast(0)
+        fwb.lib.fwb_attn_set_multicast(1)       # the default
         fwb.lib.fwb_attn_set_tail_split(1)
         fwb.lib.fwb_attn_set_variant(0)
     assert torch.equal(out, ref)

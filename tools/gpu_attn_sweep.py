@@ -64,7 +64,7 @@ for (B, H, Lq, Lk, D, name) in SHAPES:
             for on in (0, 1):
                 lib.fwb_attn_set_multicast(on)
                 ab[on].append(fl / timeit(lambda: fwb200.attention(q, k, v, out=o), iters=6) / 1e9)
-        lib.fwb_attn_set_multicast(0)
+        lib.fwb_attn_set_multicast(1)
         emit(f"   [{name}] multicast off: " + "/".join(f"{x:.0f}" for x in ab[0]) + "   on: " + "/".join(f"{x:.0f}" for x in ab[1]) + " TF")
     if D == 96:     # native PV width A/B on the default kernel
         lib.fwb_attn_set_variant(0)
