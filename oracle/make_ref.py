@@ -10,7 +10,7 @@ the GPU box, but `oracle/_ref/` (git-ignored, NOT gpurun-ignored, exactly like a
 every `gpurun` snapshot.  This script copies the reference's Python sources byte for byte — no edits — into
 `oracle/_ref/`, and writes a manifest (sha256 per file + the reference commit) so that a parity run can state exactly
 what it compared against.  Nothing under `oracle/_ref/` is ever committed and nothing in the product path reads it: only
-oracle/ref_shim.py (used by tests/, bench.py's reference legs and the golden generators) puts it on sys.path.
+tools/ref_shim.py (used by oracle/ref_runner.py — i.e. tests/ and bench.py's reference legs — and by the golden generators) puts it on sys.path.
 """
 from __future__ import annotations
 

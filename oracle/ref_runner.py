@@ -1,4 +1,4 @@
-"""oracle/ref_runner.py — runs the UNMODIFIED reference (oracle/_ref or /root/reference, through oracle/ref_shim.py) in its
+"""oracle/ref_runner.py — runs the UNMODIFIED reference (oracle/_ref or /root/reference, through tools/ref_shim.py) in its
 own process, on the CPU or on the GPU box's B200.  TEST / BENCH INFRASTRUCTURE ONLY; nothing in the product path imports it.
 
 Why a separate process: the reference's package is called `FantasyWorld`, exactly like this repo's drop-in mirror, and it
@@ -45,7 +45,7 @@ def _load_by_path(name, path):
 # neither the repo root nor fantasy-world_b200/ may be on sys.path here (the mirror package would shadow the reference)
 sys.path[:] = [p for p in sys.path if Path(p or ".").resolve() not in (ROOT, ROOT / "fantasy-world_b200")]
 S = _load_by_path("fwb_synth", ROOT / "fantasy-world_b200" / "fwb_synth.py")
-shim = _load_by_path("fwb_ref_shim", HERE / "ref_shim.py")
+shim = _load_by_path("fwb_ref_shim", ROOT / "tools" / "ref_shim.py")
 
 import torch  # noqa: E402
 
