@@ -41,6 +41,7 @@ struct AttnParams {
   __nv_bfloat16* out;
   long long o_sb, o_sl, o_sh;
   int Lq, Lk, d_real;
+  int short_kv;      // 1: one 128-row Q tile per CTA, two CTAs per SM (few KV tiles: prologue / epilogue dominate), nq counts 128-row blocks
   int pv_n;          // N of the PV MMAs: head_dim of the kernel instance, or 96 for head_dim 96 on the 128 instance (native width)
   float scale_log2;
   int accumulate;  // out = bf16(out + bf16(result))  (sum of two attentions sharing q: wan_video_dit.py:197-200)
@@ -179,16 +180,24 @@ __device__ __forceinline__ float softmax_exp(const uint32_t (&v)[N], float sl2, 
 // with `.multicast::cluster`, so a K/V tile crosses the L2 -> SM fabric once per pair instead of once per CTA (the kernel re-reads
 // every K/V tile from L2 for each of the 128 query blocks of a head: 86 GB per DiT self-attention, profiles/r02_attn_d128.md), and a
 // stage is refilled only when both CTAs' MMAs have released it (empty barriers count 2, commits multicast to both CTAs).
-template <int D, int POLY, bool MC>
+// NQ = Q tiles (128 rows each) per CTA.  2: the long-sequence configuration (two tiles ping-pong on one tensor pipe).  1: the
+// short-key configuration — half the TMEM (S | O = 256 columns), one K and one V stage, 192 threads — so that TWO CTAs are resident
+// per SM: with 2 - 13 KV tiles per CTA the prologue (barriers, TMEM, Q / first K load) and the epilogue are up to half of a CTA's
+// life, and a second resident CTA runs its main loop under them (and plays the part of the second Q tile in between).
+template <int D, int POLY, bool MC, int NQ>
 __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnParams& p) {
   using Cfg = AttnCfg<D>;
+  static_assert(NQ == 1 || NQ == 2, "one or two Q tiles per CTA");
+  static_assert(!MC || NQ == 2, "multicast pairs use the two-tile configuration");
   static_assert(!MC || Cfg::kBoxes == 2, "multicast pairs: one 64-column box per CTA (head_dim 128 instance)");
   const uint32_t crank = MC ? cluster_ctarank() : 0;
-  constexpr int ST = Cfg::kStages;
+  constexpr int ST = (NQ == 2) ? Cfg::kStages : Cfg::kStages / 2;   // NQ 1: 1 stage at head_dim 128, 2 at 64 (two CTAs share the SM's smem)
+  constexpr uint32_t kMmaWarp = 4 * NQ, kTmaWarp = 4 * NQ + 1;
+  constexpr uint32_t kColO = NQ * 128;                                // S_i at i*128, O_i at NQ*128 + i*D
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                   // [2][kTileBytes]
-  uint8_t* sK = smem + 2 * Cfg::kTileBytes;             // [ST][kTileBytes]
+  uint8_t* sQ = smem;                                   // [NQ][kTileBytes]
+  uint8_t* sK = smem + NQ * Cfg::kTileBytes;            // [ST][kTileBytes]
   uint8_t* sV = sK + ST * Cfg::kTileBytes;              // [ST][kTileBytes]
   __shared__ uint64_t q_full[2], k_full[ST], k_empty[ST], v_full[ST], v_empty[ST], s_full[2], p_full[2], o_full[2];
   __shared__ uint32_t tmem_base_s;
@@ -220,7 +229,7 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmQ, const CUte
   }
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NQ; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);  // one arrive per softmax warp
@@ -237,8 +246,8 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmQ, const CUte
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
   }
-  if (warp == 8) {
-    tmem_alloc(&tmem_base_s, 512);
+  if (warp == kMmaWarp) {
+    tmem_alloc(&tmem_base_s, 256 * NQ);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -247,13 +256,13 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmQ, const CUte
   if constexpr (MC) cluster_sync_all();   // the peer's barriers exist before any multicast load / commit targets them
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == 9) {
+  if (warp == kTmaWarp) {
     // ------------------------------------ TMA producer ------------------------------------
     if (elect_one()) {
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < NQ; ++i) {
         mbar_arrive_expect_tx(&q_full[i], Cfg::kTileBytes);
         for (int b = 0; b < Cfg::kBoxes; ++b)
-          tma_load_4d(sQ + i * Cfg::kTileBytes + b * 16384, &tmQ, &q_full[i], b * 64, head, (qblock * 2 + i) * BQ,
+          tma_load_4d(sQ + i * Cfg::kTileBytes + b * 16384, &tmQ, &q_full[i], b * 64, head, (qblock * NQ + i) * BQ,
                       batch);
       }
       for (int j = 0; j < n_kv; ++j) {
@@ -276,7 +285,7 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmQ, const CUte
         }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------ MMA issuer --------------------------------------
     if (elect_one()) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);
@@ -295,7 +304,7 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmQ, const CUte
       };
       auto issue_pv = [&](int i, uint32_t vs, bool acc) {
         const uint32_t va = v_addr + vs * Cfg::kTileBytes;
-        const uint32_t d_tmem = tmem_base + Cfg::kColO + i * D;
+        const uint32_t d_tmem = tmem_base + kColO + i * D;
         const uint32_t a_tmem = tmem_base + Cfg::kColS + i * 128;
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
@@ -314,22 +323,24 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmQ, const CUte
       tc_fence_after();
       issue_qk(0, 0);
       tc_commit(&s_full[0]);
-      mbar_wait(&q_full[1], 0);
-      tc_fence_after();
-      issue_qk(1, 0);
-      tc_commit(&s_full[1]);
+      if constexpr (NQ == 2) {
+        mbar_wait(&q_full[1], 0);
+        tc_fence_after();
+        issue_qk(1, 0);
+        tc_commit(&s_full[1]);
+      }
       release(&k_empty[0]);
 
       for (int j = 0; j < n_kv; ++j) {
         const uint32_t vs = j % ST, vph = (j / ST) & 1;
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NQ; ++i) {
           TRACE1(8, j, i * 3 + 0);
           mbar_wait(&p_full[i], j & 1);
           TRACE1(8, j, i * 3 + 1);
           if (i == 0) mbar_wait(&v_full[vs], vph);
           tc_fence_after();
           issue_pv(i, vs, j > 0);
-          if (i == 1) release(&v_empty[vs]);
+          if (i == NQ - 1) release(&v_empty[vs]);
           if (j + 1 < n_kv) {
             const uint32_t ks = (j + 1) % ST, kph = ((j + 1) / ST) & 1;
             if (i == 0) {
@@ -338,7 +349,7 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmQ, const CUte
             }
             issue_qk(i, ks);  // overwrites S_i/P_i: ordered after PV_i(j) by in-order MMA execution
             tc_commit(&s_full[i]);
-            if (i == 1) release(&k_empty[ks]);
+            if (i == NQ - 1) release(&k_empty[ks]);
           } else {
             tc_commit(&o_full[i]);
           }
@@ -352,12 +363,12 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmQ, const CUte
     const uint32_t quad = warp & 3;          // TMEM lane quadrant
     const uint32_t lane_off = (quad * 32) << 16;
     const uint32_t s_tmem = tmem_base + Cfg::kColS + i * 128 + lane_off;
-    const uint32_t o_tmem = tmem_base + Cfg::kColO + i * D + lane_off;
+    const uint32_t o_tmem = tmem_base + kColO + i * D + lane_off;
     const float sl2 = p.scale_log2;
     float m_used = -INFINITY;  // running (stale-tolerant) row max in scaled log2 units
     float l_sum = 0.f;
     // optional MUFU ping-pong between warp w (Q tile 0) and warp w+4 (Q tile 1), as in attn2_kernel
-    const bool pingpong = g_attn1_pingpong != 0;
+    const bool pingpong = NQ == 2 && g_attn1_pingpong != 0;
     const uint32_t bar_mine = 1 + quad + 4 * i, bar_other = 1 + quad + 4 * (1 - i);
     if (pingpong && i == 1) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");
 
@@ -439,7 +450,7 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmQ, const CUte
     // epilogue: O / l  -> bf16 -> global
     mbar_wait(&o_full[i], 0);
     tc_fence_after();
-    const int row = (qblock * 2 + i) * BQ + quad * 32 + lane;
+    const int row = (qblock * NQ + i) * BQ + quad * 32 + lane;
     const float inv_l = 1.f / l_sum;
     __nv_bfloat16* orow = p.out + (long long)batch * p.o_sb + (long long)row * p.o_sl + (long long)head * p.o_sh;
     const int row_in_tile = i * BQ + quad * 32 + lane;
@@ -503,21 +514,30 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmQ, const CUte
   tc_fence_before();
   __syncthreads();
   if constexpr (MC) cluster_sync_all();   // neither CTA may exit while the peer can still multicast into it or arrive on its barriers
-  if (warp == 8) tmem_dealloc(tmem_base, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 256 * NQ);
 }
 
 template <int D, int POLY>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  attn_fwd_body<D, POLY, false>(tmQ, tmK, tmV, p);
+  attn_fwd_body<D, POLY, false, 2>(tmQ, tmK, tmV, p);
 }
 
 template <int D, int POLY>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAttnThreads, 1)
 attn_fwd_mc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  attn_fwd_body<D, POLY, true>(tmQ, tmK, tmV, p);
+  attn_fwd_body<D, POLY, true, 2>(tmQ, tmK, tmV, p);
+}
+
+constexpr int kAttnShortThreads = 192;   // 4 softmax warps + MMA warp + TMA warp; two CTAs per SM
+
+template <int D, int POLY>
+__global__ void __launch_bounds__(kAttnShortThreads, 2)
+attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  attn_fwd_body<D, POLY, false, 1>(tmQ, tmK, tmV, p);
 }
 
 int make_qkv_map(CUtensorMap* m, const fwb_tensor4_t* t, int B, int H, int L, int D, int box_rows = 128) {
@@ -569,6 +589,8 @@ __global__ void attn_tail_merge_kernel(const AttnParams p, int tail) {
   }
 }
 
+int g_attn_short_max_keys = 2048;   // default policy: <= this many keys -> the one-tile, two-CTAs-per-SM configuration of the aliased kernel
+                                     // (fwb_attn_set_short_kv_max; 0 disables)
 int g_attn_multicast = 1;   // aliased kernel, head_dim 128, >= 2048 keys: CTA pairs sharing K/V tiles by TMA multicast (fwb_attn_set_multicast);
                             // bit-identical, -1.0 % step time in the in-step A/B (profiles/r02_attention.md §7)
 
@@ -576,6 +598,18 @@ template <int D, int POLY>
 int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, int B, int H,
                 cudaStream_t stream) {
   using Cfg = AttnCfg<D>;
+  if (p.short_kv) {
+    // one Q tile per CTA, half the K/V stages: Q + (K + V) x stages  (97 KB at head_dim 128, 81 KB at 64 -> two CTAs per SM)
+    constexpr int kShortSmem = Cfg::kTileBytes + 2 * (Cfg::kStages / 2) * Cfg::kTileBytes + 1024;
+    static AttrOnce once_short;
+    if (once_short.need(current_device()))
+      FWB_CUDA(cudaFuncSetAttribute(attn_fwd_short_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kShortSmem));
+    const long long tiles = (long long)p.nq * H * B;
+    FWB_CHECK(tiles < (1ll << 31), "attn: grid too large");
+    attn_fwd_short_kernel<D, POLY><<<(unsigned)tiles, kAttnShortThreads, kShortSmem, stream>>>(tq, tk, tv, p);
+    FWB_CUDA(cudaGetLastError());
+    return FWB_OK;
+  }
   static AttrOnce once;
   if (once.need(current_device()))
     FWB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -1089,6 +1123,12 @@ extern "C" int fwb_attn_set_exp2_poly(int pairs_of_8) {
   return FWB_OK;
 }
 
+extern "C" int fwb_attn_set_short_kv_max(int max_keys) {
+  FWB_CHECK(max_keys >= 0, "attn_set_short_kv_max: >= 0");
+  g_attn_short_max_keys = max_keys;
+  return FWB_OK;
+}
+
 extern "C" int fwb_attn_set_multicast(int enabled) {
   g_attn_multicast = enabled ? 1 : 0;
   return FWB_OK;
@@ -1164,7 +1204,9 @@ static int attn_impl(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_t
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = make_qkv_map(&tq, q, B, H, Lq, D))) return rc;
-  const int variant = g_attn_variant ? g_attn_variant : (D == 64 ? 2 : 1);
+  // default policy: few keys -> the short configuration of the aliased kernel (any head_dim); else decoupled at 64, aliased at 96 / 128
+  const bool short_kv = g_attn_variant == 0 && g_attn_short_max_keys > 0 && Lk <= g_attn_short_max_keys;
+  const int variant = short_kv ? 1 : (g_attn_variant ? g_attn_variant : (D == 64 ? 2 : 1));
   const int bk = (variant == 2) ? (D == 64 ? 128 : 64) : BKV;     // keys per KV tile of the kernel that will run
   if ((rc = make_qkv_map(&tk, k, B, H, Lk, D, bk))) return rc;
   if ((rc = make_qkv_map(&tv, v, B, H, Lk, D, bk))) return rc;
@@ -1180,14 +1222,15 @@ static int attn_impl(const fwb_tensor4_t* q, const fwb_tensor4_t* k, const fwb_t
   p.H = H;
   // ---- tile schedule: split the last, partly filled wave of tiles along the keys (needs a workspace; never in accumulate mode,
   // whose read-modify-write epilogue belongs to the unsplit CTA) ----
-  p.nq = (Lq + 2 * BQ - 1) / (2 * BQ);
+  p.short_kv = short_kv ? 1 : 0;
+  p.nq = short_kv ? (Lq + BQ - 1) / BQ : (Lq + 2 * BQ - 1) / (2 * BQ);
   const long long n_tiles = (long long)p.nq * H * B;
   FWB_CHECK(n_tiles < (1ll << 30), "attn: too many tiles");
   p.n_full = (int)n_tiles;
   p.S = 1;
   p.ws_out = nullptr;
   p.ws_lse = nullptr;
-  if (ws && !accumulate && g_attn_tail_split && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
+  if (!short_kv && ws && !accumulate && g_attn_tail_split && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
     int n_full = 0, S = 1;
     attn_plan(n_tiles, Lk, D, ws_bytes, num_sms(), &n_full, &S);
     if (S >= 2) {

@@ -56,6 +56,7 @@ def _load():
     lib.fwb_attn_set_mufu_pingpong.argtypes = [i32, i32]
     lib.fwb_attn_set_pv_n96.argtypes = [i32]
     lib.fwb_attn_set_multicast.argtypes = [i32]
+    lib.fwb_attn_set_short_kv_max.argtypes = [i32]
     lib.fwb_attn_fwd.argtypes = [C.POINTER(Tensor4)] * 4 + [i32, i32, i32, i32, i32, f32, i32, vp, C.c_size_t, vp]
     lib.fwb_attn_fwd_partial.argtypes = [C.POINTER(Tensor4)] * 3 + [vp, vp, i32, i32, i32, i32, i32, f32, vp, C.c_size_t, vp]
     lib.fwb_attn_merge.argtypes = [vp, vp, C.POINTER(Tensor4), i32, i32, i32, i32, i32, vp]

@@ -134,6 +134,9 @@ int fwb_attn_set_pv_n96(int enabled);
  * adjacent query blocks of one head that share every K/V tile through TMA multicast (halves the L2 -> SM traffic); bit-identical
  * results; default on (0 = off for the A/B) */
 int fwb_attn_set_multicast(int enabled);
+/* default kernel policy: problems with at most max_keys keys run the aliased kernel with ONE 128-row Q tile per CTA and two CTAs per SM
+ * (prologue / epilogue of one CTA overlap the main loop of the other); 0 disables, default 2048 */
+int fwb_attn_set_short_kv_max(int max_keys);
 
 /* ---- K7: LayerNorm (+affine) (+modulate) -> bf16 ------------------------------------------------------------------
  * out[r,:] = bf16( (LN(x[r,:]) * w + b) * mul + add ), any of (w,b), mul, add may be NULL.  fp32 statistics.

@@ -412,3 +412,33 @@ def test_attention_multicast_pairs_bit_identical(fwb, B, H, Lq, Lk, D):
     assert torch.equal(out, ref)
     assert torch.equal(part[1], part[0]) and torch.equal(lse[1], lse[0])
     torch.testing.assert_close(out.float(), _attn_ref(q, k, v), rtol=2e-2, atol=6e-3)
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,D,acc", [(1, 40, 2000, 512, 128, 0), (1, 40, 2000, 257, 128, 1), (21, 16, 1565, 1565, 64, 0), (1, 12, 700, 1565, 96, 0),
+                                             (2, 3, 129, 1, 128, 0), (1, 2, 128, 2048, 64, 0)])
+def test_attention_short_kv_configuration_bit_identical(fwb, B, H, Lq, Lk, D, acc):
+    """fwb_attn_set_short_kv_max: with few keys the default policy runs the aliased kernel with one 128-row Q tile per CTA and two CTAs
+    per SM (prologue / epilogue overlap).  A row's arithmetic does not depend on how rows are grouped into CTAs: the output (bf16,
+    accumulate mode, fp32 partial + lse) must equal the two-tile configuration's bit for bit."""
+    torch.manual_seed(Lq + Lk + D)
+    q, k, v = (_bf(torch.randn(B, L, H, D, device="cuda")) for L in (Lq, Lk, Lk))
+    base = _bf(torch.randn(B, Lq, H, D, device="cuda"))
+    part = torch.empty(2, B, Lq, H, D, device="cuda")
+    lse = torch.empty(2, B, H, Lq, device="cuda")
+    try:
+        fwb.lib.fwb_attn_set_short_kv_max(0)
+        fwb.lib.fwb_attn_set_variant(1)
+        ref = fwb.attention(q, k, v, out=base.clone(), accumulate=bool(acc))
+        fwb.attention_partial(q, k, v, part[0], lse[0])
+        fwb.lib.fwb_attn_set_variant(0)
+        fwb.lib.fwb_attn_set_short_kv_max(4096)
+        out = fwb.attention(q, k, v, out=base.clone(), accumulate=bool(acc))
+        fwb.attention_partial(q, k, v, part[1], lse[1])
+        torch.cuda.synchronize()
+    finally:
+        fwb.lib.fwb_attn_set_short_kv_max(2048)
+        fwb.lib.fwb_attn_set_variant(0)
+    assert torch.equal(out, ref)
+    assert torch.equal(part[1], part[0]) and torch.equal(lse[1], lse[0])
+    if not acc:
+        torch.testing.assert_close(out.float(), _attn_ref(q, k, v), rtol=2e-2, atol=6e-3)

@@ -29,7 +29,7 @@ def timeit(fn, iters=4, warm=1):
 
 
 SHAPES = [(1, 40, 32760, 32760, 128, "DiT self"), (1, 12, 32760, 32865, 96, "adapter v<-g"), (1, 16, 32865, 32865, 64, "VGGT global"),
-          (21, 16, 1565, 1565, 64, "VGGT frame"), (1, 40, 32760, 512, 128, "cross text"), (1, 40, 8190, 32760, 128, "DiT self, 4-rank shard")]
+          (21, 16, 1565, 1565, 64, "VGGT frame"), (1, 40, 32760, 512, 128, "cross text"), (1, 40, 32760, 257, 128, "cross CLIP"), (1, 40, 8190, 32760, 128, "DiT self, 4-rank shard")]
 if QUICK:
     SHAPES = SHAPES[:3]
 log = open(ROOT / "gpurun_out" / "r02_attn_sweep.log", "w")
@@ -66,6 +66,16 @@ for (B, H, Lq, Lk, D, name) in SHAPES:
                 ab[on].append(fl / timeit(lambda: fwb200.attention(q, k, v, out=o), iters=6) / 1e9)
         lib.fwb_attn_set_multicast(1)
         emit(f"   [{name}] multicast off: " + "/".join(f"{x:.0f}" for x in ab[0]) + "   on: " + "/".join(f"{x:.0f}" for x in ab[1]) + " TF")
+    if Lk <= 2048:     # short-key configuration (one Q tile per CTA, two CTAs per SM) A/B under the default policy
+        lib.fwb_attn_set_variant(0)
+        lib.fwb_attn_set_exp2_poly(-1)
+        ab = {0: [], 2048: []}
+        for rnd in range(4):
+            for mx in (0, 2048):
+                lib.fwb_attn_set_short_kv_max(mx)
+                ab[mx].append(fl / timeit(lambda: fwb200.attention(q, k, v, out=o), iters=6) / 1e9)
+        lib.fwb_attn_set_short_kv_max(2048)
+        emit(f"   [{name}] short-kv config off: " + "/".join(f"{x:.0f}" for x in ab[0]) + "   on: " + "/".join(f"{x:.0f}" for x in ab[2048]) + " TF")
     if D == 96:     # native PV width A/B on the default kernel
         lib.fwb_attn_set_variant(0)
         lib.fwb_attn_set_exp2_poly(-1)
