@@ -304,3 +304,15 @@ class WanVideoVAE(nn.Module):
         if tiled:
             return self.tiled_decode(hidden_states, device, tile_size, tile_stride, group=group)
         return self.single_decode(hidden_states, device)
+
+    @staticmethod
+    def state_dict_converter():
+        return WanVideoVAEStateDictConverter()
+
+
+class WanVideoVAEStateDictConverter:
+    """ref: :789-800 — `Wan2.1_VAE.pth` holds the bare VideoVAE_ keys (optionally under 'model_state'): prefix with `model.`."""
+
+    def from_civitai(self, state_dict):
+        inner = state_dict.get("model_state", state_dict)
+        return {"model." + k: v for k, v in inner.items()}
