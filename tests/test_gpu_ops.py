@@ -272,6 +272,9 @@ def test_attention_softmax_rows_sum_to_one_full_size(fwb):
 # ------------------------------------------------------------------------------------------------------------------
 # row kernels
 # ------------------------------------------------------------------------------------------------------------------
+ROW_RING_DEFAULT = 0      # the library default of fwb_rowwise_set_ring (restored after the A/B test)
+
+
 @pytest.mark.parametrize("rows,C,dtype", [(37, 5120, torch.bfloat16), (50, 1024, torch.float32), (9, 1280, torch.bfloat16),
                                           (5, 2048, torch.float32), (3, 2560, torch.bfloat16)])
 def test_ln_modulate(fwb, rows, C, dtype):
@@ -310,6 +313,48 @@ def test_rmsnorm_rope(fwb):
     ref = O.rope_apply(orig[:, :1152].float().cpu()[None], tab96, 12, O.BF16)[0]
     assert_close_frac(buf[:, :1152].float().cpu(), ref, rtol=1.6e-2, atol=1.6e-2, loose_atol=1.3e-1)
     assert torch.equal(buf[:, 1152:], orig[:, 1152:])
+
+
+@pytest.mark.parametrize("rows,C,dtype", [(2000, 5120, torch.float32), (2000, 5120, torch.bfloat16), (4097, 1024, torch.float32),
+                                          (1300, 2048, torch.bfloat16), (7, 5120, torch.float32), (1, 64, torch.bfloat16),
+                                          (5000, 1280, torch.bfloat16)])
+def test_row_kernels_bulk_copy_ring_bit_identical(fwb, rows, C, dtype):
+    """fwb_rowwise_set_ring: rows streamed into a 3-deep shared-memory ring by cp.async.bulk instead of the register prefetch.  Same
+    element ownership and reduction order -> the outputs must be equal bit for bit, for every row count relative to the grid
+    (fewer rows than CTAs, not a multiple of the grid, many rows per CTA), strided rows and the in-place kernel."""
+    torch.manual_seed(rows + C)
+    x = (torch.randn(rows, C, device="cuda") * 2 + 0.3).to(dtype)
+    wide = (torch.randn(rows, 2 * C + 8, device="cuda")).to(dtype)           # rows with a stride != C, 16-byte aligned start
+    w, b, mul, add = (torch.randn(C, device="cuda") for _ in range(4))
+    hd = 128 if C % 128 == 0 else 64
+    cs = torch.randn(rows, hd // 2, 2, device="cuda")
+    wt = torch.rand(C, device="cuda") + 0.5
+
+    def run():
+        outs = []
+        for kw in (dict(), dict(w=w, b=b), dict(mul=mul, add=add), dict(w=w, b=b, mul=mul, add=add)):
+            outs.append(fwb.ln_modulate(x, eps=1e-6, **kw))
+        outs.append(fwb.ln_modulate(wide[:, 8:8 + C], eps=1e-5, w=w, b=b))
+        if dtype == torch.bfloat16:
+            for kw in (dict(w=wt, cos_sin=cs, head_dim=hd), dict(cos_sin=cs, head_dim=hd), dict(w=wt)):
+                y = x.clone()
+                fwb.rmsnorm_rope_(y, eps=1e-6, **kw)
+                outs.append(y)
+            buf = wide.clone()
+            fwb.rmsnorm_rope_(buf[:, 8:8 + C], w=wt, eps=1e-6, cos_sin=cs, head_dim=hd)
+            outs.append(buf)
+        torch.cuda.synchronize()
+        return outs
+
+    try:
+        fwb.lib.fwb_rowwise_set_ring(0)
+        ref = run()
+        fwb.lib.fwb_rowwise_set_ring(1)
+        out = run()
+    finally:
+        fwb.lib.fwb_rowwise_set_ring(ROW_RING_DEFAULT)
+    for a, r in zip(out, ref):
+        assert torch.equal(a, r)
 
 
 def test_ln64_rope2d(fwb):

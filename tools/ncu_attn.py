@@ -22,4 +22,17 @@ elif kind == "gemm":
     b = torch.randn(N, device="cuda")
     for _ in range(3):
         fwb200.linear(x, w, bias=b)
+elif kind == "ln":                      # DiT pre-attention / pre-FFN LayerNorm + modulation: fp32 residual stream -> bf16
+    rows, C = 32760, 5120
+    x = torch.randn(rows, C, device="cuda")
+    mul, add = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+    for _ in range(3):
+        fwb200.ln_modulate(x, eps=1e-6, mul=mul, add=add)
+elif kind == "rms":                     # q / k RMSNorm + RoPE, in place on bf16
+    rows, C, hd = 32760, 5120, 128
+    x = torch.randn(rows, C, device="cuda").to(torch.bfloat16)
+    w = torch.randn(C, device="cuda")
+    cs = torch.randn(rows, hd // 2, 2, device="cuda")
+    for _ in range(3):
+        fwb200.rmsnorm_rope_(x, w=w, eps=1e-6, cos_sin=cs, head_dim=hd)
 torch.cuda.synchronize()
