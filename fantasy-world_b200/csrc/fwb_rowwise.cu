@@ -19,7 +19,7 @@ using namespace fwb;
 
 namespace {
 
-constexpr int kRowThreads = 128;
+constexpr int kRowThreads = 128;   // narrow CTAs (rows of <= 2048 elements); wide rows can run on 256 threads, see row_threads()
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -27,12 +27,16 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// block-wide sum for kRowThreads threads; `red` is a 4-float smem scratch (reused: call sites sync)
+// block-wide sum for THREADS threads; `red` is a THREADS/32-float smem scratch (reused: call sites sync).  The warp partials are
+// added in warp order (for 128 threads: ((r0 + r1) + r2) + r3, as ever).
+template <int THREADS>
 __device__ __forceinline__ float block_sum(float v, float* red) {
   v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  float t = red[0] + red[1] + red[2] + red[3];
+  float t = red[0];
+#pragma unroll
+  for (int i = 1; i < THREADS / 32; ++i) t += red[i];
   __syncthreads();
   return t;
 }
@@ -71,11 +75,11 @@ struct RowRaw {
   uint4 q[CHUNKS][IN_F32 ? 2 : 1];
 };
 
-template <int CHUNKS, bool IN_F32>
+template <int THREADS, int CHUNKS, bool IN_F32>
 __device__ __forceinline__ void row_load(RowRaw<CHUNKS, IN_F32>& r, const void* __restrict__ x, long long ldx, int row, int nchunks) {
 #pragma unroll
   for (int i = 0; i < CHUNKS; ++i) {
-    const int ch = threadIdx.x + i * kRowThreads;
+    const int ch = threadIdx.x + i * THREADS;
     if (ch < nchunks) {
       if (IN_F32) {
         const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(x) + (size_t)row * ldx + ch * 8);
@@ -99,113 +103,35 @@ __device__ __forceinline__ void row_unpack(const RowRaw<CHUNKS, IN_F32>& r, int 
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// Bulk-copy row ring (RING = true variants).  The register prefetch above keeps ONE row per CTA in flight and pays for it
-// in registers (a raw fp32 row is 40 registers per thread: 128 registers, 4 CTAs per SM — ncu: 25 % of the warps, the top
-// stall is the load scoreboard, DRAM at 61 % of peak).  Here one thread streams whole rows into a kRingStages-deep shared
-// memory ring with cp.async.bulk (one instruction per row, no registers, completion on an mbarrier), so every CTA has
-// kRingStages - 1 .. kRingStages rows of loads in flight whatever its register count.  A stage is refilled right after the
-// first block-wide barrier that follows the copy of its row into registers.  Element ownership and reduction order are
-// those of the register version: results are bit-identical.
-// ------------------------------------------------------------------------------------------------------------
-constexpr int kRingStages = 3;
-
-template <int CHUNKS, bool IN_F32>
-__device__ __forceinline__ void row_from_ring(RowRaw<CHUNKS, IN_F32>& r, const unsigned char* stage, int nchunks) {
-#pragma unroll
-  for (int i = 0; i < CHUNKS; ++i) {
-    const int ch = threadIdx.x + i * kRowThreads;
-    if (ch < nchunks) {
-      const uint4* p = reinterpret_cast<const uint4*>(stage + (size_t)ch * (IN_F32 ? 32 : 16));
-      r.q[i][0] = p[0];
-      if (IN_F32) r.q[i][IN_F32 ? 1 : 0] = p[1];
-    }
-  }
-}
-
-struct RowRing {
-  unsigned char* buf;
-  uint64_t* full;
-  const unsigned char* src;   // first row
-  size_t row_stride;          // bytes between rows in global memory
-  uint32_t row_bytes;         // bytes copied per row
-  int rows, step;
-
-  __device__ __forceinline__ void init(uint64_t* bars) {
-    full = bars;
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int s = 0; s < kRingStages; ++s) mbar_init(&full[s], 1);
-      fence_mbar_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int s = 0; s < kRingStages; ++s) fill(s, blockIdx.x + s * step);
-    }
-  }
-  // thread 0 only; the stage's previous contents have been read by every thread (a block-wide barrier lies in between)
-  __device__ __forceinline__ void fill(int stage, long long row) {
-    if (row < rows) {
-      fence_proxy_async_smem();
-      mbar_arrive_expect_tx(&full[stage], row_bytes);
-      bulk_load_1d(buf + (size_t)stage * row_bytes, src + (size_t)row * row_stride, row_bytes, &full[stage]);
-    }
-  }
-  __device__ __forceinline__ const unsigned char* wait(int it) const {
-    const int stage = it % kRingStages;
-    mbar_wait(&full[stage], (it / kRingStages) & 1);
-    return buf + (size_t)stage * row_bytes;
-  }
-};
-
-template <int CHUNKS, bool IN_F32, bool RING>
-__global__ void __launch_bounds__(kRowThreads)
+template <int THREADS, int CHUNKS, bool IN_F32>
+__global__ void __launch_bounds__(THREADS)
 ln_modulate_kernel(const void* __restrict__ x, long long ldx, int rows, int C, float eps, const float* __restrict__ w,
                    const float* __restrict__ b, const float* __restrict__ mul, const float* __restrict__ add,
                    __nv_bfloat16* __restrict__ out, long long ldo) {
-  __shared__ float red[4];
-  __shared__ uint64_t ring_bars[kRingStages];
-  extern __shared__ __align__(128) unsigned char ring_buf[];
+  __shared__ float red[THREADS / 32];
   const int nchunks = C >> 3;
   RowRaw<CHUNKS, IN_F32> cur, nxt;
-  RowRing ring;
   int row = blockIdx.x;
   if (row >= rows) return;
-  if (RING) {
-    ring.buf = ring_buf;
-    ring.src = reinterpret_cast<const unsigned char*>(x);
-    ring.row_stride = (size_t)ldx * (IN_F32 ? 4 : 2);
-    ring.row_bytes = (uint32_t)C * (IN_F32 ? 4 : 2);
-    ring.rows = rows;
-    ring.step = gridDim.x;
-    ring.init(ring_bars);
-  } else {
-    row_load(cur, x, ldx, row, nchunks);
-  }
-  for (int it = 0; row < rows; row += gridDim.x, ++it) {
-    if (RING) {
-      row_from_ring(cur, ring.wait(it), nchunks);
-    } else {
-      const int next = row + gridDim.x;
-      if (next < rows) row_load(nxt, x, ldx, next, nchunks);
-    }
+  row_load<THREADS>(cur, x, ldx, row, nchunks);
+  for (; row < rows; row += gridDim.x) {
+    const int next = row + gridDim.x;
+    if (next < rows) row_load<THREADS>(nxt, x, ldx, next, nchunks);
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < CHUNKS; ++i) {
-      if ((int)threadIdx.x + i * kRowThreads < nchunks) {
+      if ((int)threadIdx.x + i * THREADS < nchunks) {
         float v[8];
         row_unpack(cur, i, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += v[j];
       }
     }
-    const float mean = block_sum(s, red) / (float)C;
-    if (RING && threadIdx.x == 0) ring.fill(it % kRingStages, (long long)row + (long long)kRingStages * gridDim.x);
+    const float mean = block_sum<THREADS>(s, red) / (float)C;
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < CHUNKS; ++i) {
-      if ((int)threadIdx.x + i * kRowThreads < nchunks) {
+      if ((int)threadIdx.x + i * THREADS < nchunks) {
         float v[8];
         row_unpack(cur, i, v);
 #pragma unroll
@@ -215,10 +141,10 @@ ln_modulate_kernel(const void* __restrict__ x, long long ldx, int rows, int C, f
         }
       }
     }
-    const float rstd = rsqrtf(block_sum(q, red) / (float)C + eps);
+    const float rstd = rsqrtf(block_sum<THREADS>(q, red) / (float)C + eps);
 #pragma unroll
     for (int i = 0; i < CHUNKS; ++i) {
-      const int ch = threadIdx.x + i * kRowThreads;
+      const int ch = threadIdx.x + i * THREADS;
       if (ch < nchunks) {
         const int c0 = ch * 8;
         float v[8], y[8];
@@ -247,7 +173,7 @@ ln_modulate_kernel(const void* __restrict__ x, long long ldx, int rows, int C, f
         *reinterpret_cast<uint4*>(out + (size_t)row * ldo + c0) = pack8(y);
       }
     }
-    if (!RING) cur = nxt;
+    cur = nxt;
   }
 }
 
@@ -255,57 +181,38 @@ ln_modulate_kernel(const void* __restrict__ x, long long ldx, int rows, int C, f
 // RMSNorm over the full row (+weight) then RoPE on interleaved pairs, in place on bf16.
 // Rounding points follow the reference: bf16(x*rstd) -> bf16(* w) -> rope in fp32 -> bf16.
 // ------------------------------------------------------------------------------------------------------------
-template <int CHUNKS, bool RING>
-__global__ void __launch_bounds__(kRowThreads)
+template <int THREADS, int CHUNKS>
+__global__ void __launch_bounds__(THREADS)
 rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, int rows, int C, const float* __restrict__ w,
                     float eps, const float2* __restrict__ cs, int head_dim) {
-  // persistent rows with the next row(s) prefetched, as ln_modulate_kernel (in place: a row is only ever touched by one CTA)
-  __shared__ float red[4];
-  __shared__ uint64_t ring_bars[kRingStages];
-  extern __shared__ __align__(128) unsigned char ring_buf[];
+  // persistent rows with the next row prefetched, as ln_modulate_kernel (in place: a row is only ever touched by one CTA)
+  __shared__ float red[THREADS / 32];
   const int nchunks = C >> 3;
   const int half = head_dim >> 1;
   RowRaw<CHUNKS, false> cur, nxt;
-  RowRing ring;
   int row = blockIdx.x;
   if (row >= rows) return;
-  if (RING) {
-    ring.buf = ring_buf;
-    ring.src = reinterpret_cast<const unsigned char*>(x);
-    ring.row_stride = (size_t)ldx * 2;
-    ring.row_bytes = (uint32_t)C * 2;
-    ring.rows = rows;
-    ring.step = gridDim.x;
-    ring.init(ring_bars);
-  } else {
-    row_load(cur, x, ldx, row, nchunks);
-  }
-  for (int it = 0; row < rows; row += gridDim.x, ++it) {
-    if (RING) {
-      row_from_ring(cur, ring.wait(it), nchunks);
-      if (!w) __syncthreads();      // no reduction below: this is the barrier between the stage's readers and its refill
-    } else {
-      const int next = row + gridDim.x;
-      if (next < rows) row_load(nxt, x, ldx, next, nchunks);
-    }
+  row_load<THREADS>(cur, x, ldx, row, nchunks);
+  for (; row < rows; row += gridDim.x) {
+    const int next = row + gridDim.x;
+    if (next < rows) row_load<THREADS>(nxt, x, ldx, next, nchunks);
     float rstd = 1.f;
     if (w) {
       float s = 0.f;
 #pragma unroll
       for (int i = 0; i < CHUNKS; ++i) {
-        if ((int)threadIdx.x + i * kRowThreads < nchunks) {
+        if ((int)threadIdx.x + i * THREADS < nchunks) {
           float v[8];
           row_unpack(cur, i, v);
 #pragma unroll
           for (int j = 0; j < 8; ++j) s += v[j] * v[j];
         }
       }
-      rstd = rsqrtf(block_sum(s, red) / (float)C + eps);
+      rstd = rsqrtf(block_sum<THREADS>(s, red) / (float)C + eps);
     }
-    if (RING && threadIdx.x == 0) ring.fill(it % kRingStages, (long long)row + (long long)kRingStages * gridDim.x);
 #pragma unroll
     for (int i = 0; i < CHUNKS; ++i) {
-      const int ch = threadIdx.x + i * kRowThreads;
+      const int ch = threadIdx.x + i * THREADS;
       if (ch < nchunks) {
         const int c0 = ch * 8;
         float v[8], y[8];
@@ -333,7 +240,7 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, int rows, int 
         *reinterpret_cast<uint4*>(x + (size_t)row * ldx + c0) = pack8(y);
       }
     }
-    if (!RING) cur = nxt;
+    cur = nxt;
   }
 }
 
@@ -432,33 +339,27 @@ __global__ void cfg_euler_kernel(__nv_bfloat16* __restrict__ lat, const __nv_bfl
 }
 
 int g_row_ctas_per_sm = 0;   // 0 = as many as fit (occupancy query per kernel); n > 0 forces n (fwb_rowwise_set_ctas_per_sm, A/B only)
-int g_row_ring = 0;          // 1: bulk-copy row ring instead of the register prefetch (fwb_rowwise_set_ring); bit-identical results
+int g_row_wide_threads = 128;   // CTA width for rows of more than 2048 elements: 128 (5 chunks per thread) or 256 (3), fwb_rowwise_set_threads
 
 // Grid of a persistent row kernel: (resident CTAs per SM) x #SMs — exactly one wave, so no CTA waits for a slot and the rows are dealt
-// evenly (measured: a grid of 8 CTAs/SM when only 6 fit costs +27 %) — and never more than one CTA per row.  `smem` is the dynamic
-// shared memory of the launch (the ring variants; the occupancy is cached per instantiation for its LARGEST row, i.e. conservatively).
-template <auto Kernel>
-inline int row_grid(int rows, size_t smem = 0) {
+// evenly (measured: a grid of 8 CTAs/SM when only 6 fit costs +27 %) — and never more than one CTA per row.
+template <auto Kernel, int THREADS>
+inline int row_grid(int rows) {
   static int occ[64] = {0};                       // per kernel instantiation and device ordinal
-  static AttrOnce attr;
-  const int dev = current_device();
-  if (smem > 48 * 1024 && attr.need(dev)) cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = g_row_ctas_per_sm;
   if (per_sm <= 0) {
+    const int dev = current_device();
     int* slot = (dev >= 0 && dev < 64) ? &occ[dev] : nullptr;
     if (slot && *slot > 0) {
       per_sm = *slot;
     } else {
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, Kernel, kRowThreads, smem) != cudaSuccess || per_sm <= 0) per_sm = 4;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, Kernel, THREADS, 0) != cudaSuccess || per_sm <= 0) per_sm = 4;
       if (slot) *slot = per_sm;
     }
   }
   const long long g = (long long)(num_sms() > 0 ? num_sms() : 148) * per_sm;
   return (int)(g < rows ? g : rows);
 }
-
-// largest row an instantiation with CHUNKS chunks per thread can be launched on -> the ring bytes its occupancy is computed for
-constexpr size_t ring_bytes_max(int chunks, int esize) { return (size_t)kRingStages * chunks * kRowThreads * 8 * esize; }
 
 }  // namespace
 
@@ -468,9 +369,9 @@ extern "C" int fwb_rowwise_set_ctas_per_sm(int n) {
   return FWB_OK;
 }
 
-extern "C" int fwb_rowwise_set_ring(int on) {
-  FWB_CHECK(on == 0 || on == 1, "rowwise_set_ring: 0 (register prefetch) or 1 (bulk-copy row ring)");
-  g_row_ring = on;
+extern "C" int fwb_rowwise_set_threads(int n) {
+  FWB_CHECK(n == 128 || n == 256, "rowwise_set_threads: 128 or 256 threads per CTA for rows of more than 2048 elements");
+  g_row_wide_threads = n;
   return FWB_OK;
 }
 
@@ -484,22 +385,19 @@ extern "C" int fwb_ln_modulate(const void* x, int x_dtype, int64_t ldx, int rows
   FWB_CHECK((w == nullptr) == (b == nullptr), "ln_modulate: affine weight and bias must come together");
   const int chunks = (C / 8 + kRowThreads - 1) / kRowThreads;
   const bool f32 = x_dtype == FWB_DT_F32;
-  const bool ring = g_row_ring && (reinterpret_cast<uintptr_t>(x) & 15) == 0;     // bulk copies need 16-byte aligned rows
-  const size_t smem = ring ? (size_t)kRingStages * C * (f32 ? 4 : 2) : 0;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-#define LAUNCH_K(CH, F32, RING)                                                                                              \
-  ln_modulate_kernel<CH, F32, RING><<<row_grid<ln_modulate_kernel<CH, F32, RING>>(rows, RING ? ring_bytes_max(CH, F32 ? 4 : 2) : 0), \
-                                      kRowThreads, smem, stream>>>(x, ldx, rows, C, eps, w, b, mul, add, o, ldo)
-#define LAUNCH(CH)                                       \
-  do {                                                   \
-    if (f32 && ring) LAUNCH_K(CH, true, true);           \
-    else if (f32) LAUNCH_K(CH, true, false);             \
-    else if (ring) LAUNCH_K(CH, false, true);            \
-    else LAUNCH_K(CH, false, false);                     \
+#define LAUNCH_K(TH, CH, F32)                                                                                                   \
+  ln_modulate_kernel<TH, CH, F32><<<row_grid<ln_modulate_kernel<TH, CH, F32>, TH>(rows), TH, 0, stream>>>(x, ldx, rows, C, eps, w, \
+                                                                                                         b, mul, add, o, ldo)
+#define LAUNCH(TH, CH)                    \
+  do {                                    \
+    if (f32) LAUNCH_K(TH, CH, true);      \
+    else LAUNCH_K(TH, CH, false);         \
   } while (0)
-  if (chunks <= 1) LAUNCH(1);
-  else if (chunks <= 2) LAUNCH(2);
-  else LAUNCH(5);
+  if (chunks <= 1) LAUNCH(128, 1);
+  else if (chunks <= 2) LAUNCH(128, 2);
+  else if (g_row_wide_threads == 256) LAUNCH(256, 3);
+  else LAUNCH(128, 5);
 #undef LAUNCH
 #undef LAUNCH_K
   FWB_CUDA(cudaGetLastError());
@@ -515,21 +413,14 @@ extern "C" int fwb_rmsnorm_rope(void* x, int64_t ldx, int rows, int C, const flo
   const int chunks = (C / 8 + kRowThreads - 1) / kRowThreads;
   __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(x);
   const float2* cs = reinterpret_cast<const float2*>(cos_sin);
-  const bool ring = g_row_ring && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-  const size_t smem = ring ? (size_t)kRingStages * C * 2 : 0;
-#define LAUNCH_K(CH, RING)                                                                                             \
-  rmsnorm_rope_kernel<CH, RING><<<row_grid<rmsnorm_rope_kernel<CH, RING>>(rows, RING ? ring_bytes_max(CH, 2) : 0), kRowThreads, \
-                                  smem, stream>>>(xp, ldx, rows, C, w, eps, cs, head_dim)
-#define LAUNCH(CH)                   \
-  do {                               \
-    if (ring) LAUNCH_K(CH, true);    \
-    else LAUNCH_K(CH, false);        \
-  } while (0)
-  if (chunks <= 1) LAUNCH(1);
-  else if (chunks <= 2) LAUNCH(2);
-  else LAUNCH(5);
+#define LAUNCH(TH, CH)                                                                                                        \
+  rmsnorm_rope_kernel<TH, CH><<<row_grid<rmsnorm_rope_kernel<TH, CH>, TH>(rows), TH, 0, stream>>>(xp, ldx, rows, C, w, eps, cs, \
+                                                                                                  head_dim)
+  if (chunks <= 1) LAUNCH(128, 1);
+  else if (chunks <= 2) LAUNCH(128, 2);
+  else if (g_row_wide_threads == 256) LAUNCH(256, 3);
+  else LAUNCH(128, 5);
 #undef LAUNCH
-#undef LAUNCH_K
   FWB_CUDA(cudaGetLastError());
   return FWB_OK;
 }

@@ -272,7 +272,7 @@ def test_attention_softmax_rows_sum_to_one_full_size(fwb):
 # ------------------------------------------------------------------------------------------------------------------
 # row kernels
 # ------------------------------------------------------------------------------------------------------------------
-ROW_RING_DEFAULT = 0      # the library default of fwb_rowwise_set_ring (restored after the A/B test)
+ROW_WIDE_THREADS_DEFAULT = 128      # the library default of fwb_rowwise_set_threads (restored after the A/B test)
 
 
 @pytest.mark.parametrize("rows,C,dtype", [(37, 5120, torch.bfloat16), (50, 1024, torch.float32), (9, 1280, torch.bfloat16),
@@ -315,18 +315,17 @@ def test_rmsnorm_rope(fwb):
     assert torch.equal(buf[:, 1152:], orig[:, 1152:])
 
 
-@pytest.mark.parametrize("rows,C,dtype", [(2000, 5120, torch.float32), (2000, 5120, torch.bfloat16), (4097, 1024, torch.float32),
-                                          (1300, 2048, torch.bfloat16), (7, 5120, torch.float32), (1, 64, torch.bfloat16),
-                                          (5000, 1280, torch.bfloat16)])
-def test_row_kernels_bulk_copy_ring_bit_identical(fwb, rows, C, dtype):
-    """fwb_rowwise_set_ring: rows streamed into a 3-deep shared-memory ring by cp.async.bulk instead of the register prefetch.  Same
-    element ownership and reduction order -> the outputs must be equal bit for bit, for every row count relative to the grid
-    (fewer rows than CTAs, not a multiple of the grid, many rows per CTA), strided rows and the in-place kernel."""
+@pytest.mark.parametrize("rows,C,dtype", [(2000, 5120, torch.float32), (2000, 5120, torch.bfloat16), (1300, 2560, torch.bfloat16),
+                                          (7, 5120, torch.float32), (1, 2056, torch.bfloat16), (900, 3072, torch.float32)])
+def test_row_kernels_256_thread_ctas(fwb, rows, C, dtype):
+    """fwb_rowwise_set_threads: rows of more than 2048 elements on 256-thread CTAs (3 chunks per thread) instead of 128 (5 chunks).
+    The element-to-thread mapping changes the fp32 summation order of the row statistics, so the two are compared with each other at
+    one bf16 ulp on a vanishing fraction of elements, and each with the fp32 reference; strided rows and the in-place kernel included."""
     torch.manual_seed(rows + C)
     x = (torch.randn(rows, C, device="cuda") * 2 + 0.3).to(dtype)
-    wide = (torch.randn(rows, 2 * C + 8, device="cuda")).to(dtype)           # rows with a stride != C, 16-byte aligned start
+    wide = (torch.randn(rows, 2 * C + 8, device="cuda")).to(dtype)           # rows with a stride != C
     w, b, mul, add = (torch.randn(C, device="cuda") for _ in range(4))
-    hd = 128 if C % 128 == 0 else 64
+    hd = 128 if C % 128 == 0 else 8
     cs = torch.randn(rows, hd // 2, 2, device="cuda")
     wt = torch.rand(C, device="cuda") + 0.5
 
@@ -347,14 +346,19 @@ def test_row_kernels_bulk_copy_ring_bit_identical(fwb, rows, C, dtype):
         return outs
 
     try:
-        fwb.lib.fwb_rowwise_set_ring(0)
+        fwb.lib.fwb_rowwise_set_threads(128)
         ref = run()
-        fwb.lib.fwb_rowwise_set_ring(1)
+        fwb.lib.fwb_rowwise_set_threads(256)
         out = run()
     finally:
-        fwb.lib.fwb_rowwise_set_ring(ROW_RING_DEFAULT)
+        fwb.lib.fwb_rowwise_set_threads(ROW_WIDE_THREADS_DEFAULT)
+    y = torch.nn.functional.layer_norm(x.float(), (C,), w, b, 1e-6) * mul + add
+    torch.testing.assert_close(out[3].float(), y.to(torch.bfloat16).float(), rtol=8e-3, atol=1e-2)
     for a, r in zip(out, ref):
-        assert torch.equal(a, r)
+        assert_close_frac(a, r, rtol=0, atol=0, loose_atol=0.13, max_bad_frac=2e-3)      # a few rounding ties may fall the other way
+        assert a.shape == r.shape
+    if dtype == torch.bfloat16:      # rope-only (no statistics) does not depend on the mapping at all
+        assert torch.equal(out[6], ref[6])
 
 
 def test_ln64_rope2d(fwb):
