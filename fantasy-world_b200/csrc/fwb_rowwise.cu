@@ -19,7 +19,7 @@ using namespace fwb;
 
 namespace {
 
-constexpr int kRowThreads = 128;   // narrow CTAs (rows of <= 2048 elements); wide rows can run on 256 threads, see row_threads()
+constexpr int kRowThreads = 128;
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -27,18 +27,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// block-wide sum for THREADS threads; `red` is a THREADS/32-float smem scratch (reused: call sites sync).  The warp partials are
-// added in warp order (for 128 threads: ((r0 + r1) + r2) + r3, as ever).
-template <int THREADS>
+// block-wide sum for kRowThreads threads through a 4-float smem scratch, ONE barrier.  The scratch is not protected against the
+// next call: consecutive reductions must alternate between two scratch buffers (a thread can only overwrite buffer A after the
+// barrier of the reduction on buffer B, which every thread reaches after it has read A).
 __device__ __forceinline__ float block_sum(float v, float* red) {
   v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  float t = red[0];
-#pragma unroll
-  for (int i = 1; i < THREADS / 32; ++i) t += red[i];
-  __syncthreads();
-  return t;
+  return red[0] + red[1] + red[2] + red[3];
 }
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
@@ -75,11 +71,11 @@ struct RowRaw {
   uint4 q[CHUNKS][IN_F32 ? 2 : 1];
 };
 
-template <int THREADS, int CHUNKS, bool IN_F32>
+template <int CHUNKS, bool IN_F32>
 __device__ __forceinline__ void row_load(RowRaw<CHUNKS, IN_F32>& r, const void* __restrict__ x, long long ldx, int row, int nchunks) {
 #pragma unroll
   for (int i = 0; i < CHUNKS; ++i) {
-    const int ch = threadIdx.x + i * THREADS;
+    const int ch = threadIdx.x + i * kRowThreads;
     if (ch < nchunks) {
       if (IN_F32) {
         const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(x) + (size_t)row * ldx + ch * 8);
@@ -103,35 +99,35 @@ __device__ __forceinline__ void row_unpack(const RowRaw<CHUNKS, IN_F32>& r, int 
   }
 }
 
-template <int THREADS, int CHUNKS, bool IN_F32>
-__global__ void __launch_bounds__(THREADS)
+template <int CHUNKS, bool IN_F32>
+__global__ void __launch_bounds__(kRowThreads)
 ln_modulate_kernel(const void* __restrict__ x, long long ldx, int rows, int C, float eps, const float* __restrict__ w,
                    const float* __restrict__ b, const float* __restrict__ mul, const float* __restrict__ add,
                    __nv_bfloat16* __restrict__ out, long long ldo) {
-  __shared__ float red[THREADS / 32];
+  __shared__ float red[4], red2[4];     // mean / variance reductions alternate (see block_sum)
   const int nchunks = C >> 3;
   RowRaw<CHUNKS, IN_F32> cur, nxt;
   int row = blockIdx.x;
   if (row >= rows) return;
-  row_load<THREADS>(cur, x, ldx, row, nchunks);
+  row_load(cur, x, ldx, row, nchunks);
   for (; row < rows; row += gridDim.x) {
     const int next = row + gridDim.x;
-    if (next < rows) row_load<THREADS>(nxt, x, ldx, next, nchunks);
+    if (next < rows) row_load(nxt, x, ldx, next, nchunks);
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < CHUNKS; ++i) {
-      if ((int)threadIdx.x + i * THREADS < nchunks) {
+      if ((int)threadIdx.x + i * kRowThreads < nchunks) {
         float v[8];
         row_unpack(cur, i, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += v[j];
       }
     }
-    const float mean = block_sum<THREADS>(s, red) / (float)C;
+    const float mean = block_sum(s, red) / (float)C;
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < CHUNKS; ++i) {
-      if ((int)threadIdx.x + i * THREADS < nchunks) {
+      if ((int)threadIdx.x + i * kRowThreads < nchunks) {
         float v[8];
         row_unpack(cur, i, v);
 #pragma unroll
@@ -141,10 +137,10 @@ ln_modulate_kernel(const void* __restrict__ x, long long ldx, int rows, int C, f
         }
       }
     }
-    const float rstd = rsqrtf(block_sum<THREADS>(q, red) / (float)C + eps);
+    const float rstd = rsqrtf(block_sum(q, red2) / (float)C + eps);
 #pragma unroll
     for (int i = 0; i < CHUNKS; ++i) {
-      const int ch = threadIdx.x + i * THREADS;
+      const int ch = threadIdx.x + i * kRowThreads;
       if (ch < nchunks) {
         const int c0 = ch * 8;
         float v[8], y[8];
@@ -181,38 +177,40 @@ ln_modulate_kernel(const void* __restrict__ x, long long ldx, int rows, int C, f
 // RMSNorm over the full row (+weight) then RoPE on interleaved pairs, in place on bf16.
 // Rounding points follow the reference: bf16(x*rstd) -> bf16(* w) -> rope in fp32 -> bf16.
 // ------------------------------------------------------------------------------------------------------------
-template <int THREADS, int CHUNKS>
-__global__ void __launch_bounds__(THREADS)
+template <int CHUNKS>
+__global__ void __launch_bounds__(kRowThreads)
 rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, int rows, int C, const float* __restrict__ w,
                     float eps, const float2* __restrict__ cs, int head_dim) {
   // persistent rows with the next row prefetched, as ln_modulate_kernel (in place: a row is only ever touched by one CTA)
-  __shared__ float red[THREADS / 32];
+  __shared__ float red[2][4];           // one reduction per row: alternate by row (see block_sum)
+  int flip = 0;
   const int nchunks = C >> 3;
   const int half = head_dim >> 1;
   RowRaw<CHUNKS, false> cur, nxt;
   int row = blockIdx.x;
   if (row >= rows) return;
-  row_load<THREADS>(cur, x, ldx, row, nchunks);
+  row_load(cur, x, ldx, row, nchunks);
   for (; row < rows; row += gridDim.x) {
     const int next = row + gridDim.x;
-    if (next < rows) row_load<THREADS>(nxt, x, ldx, next, nchunks);
+    if (next < rows) row_load(nxt, x, ldx, next, nchunks);
     float rstd = 1.f;
     if (w) {
       float s = 0.f;
 #pragma unroll
       for (int i = 0; i < CHUNKS; ++i) {
-        if ((int)threadIdx.x + i * THREADS < nchunks) {
+        if ((int)threadIdx.x + i * kRowThreads < nchunks) {
           float v[8];
           row_unpack(cur, i, v);
 #pragma unroll
           for (int j = 0; j < 8; ++j) s += v[j] * v[j];
         }
       }
-      rstd = rsqrtf(block_sum<THREADS>(s, red) / (float)C + eps);
+      rstd = rsqrtf(block_sum(s, red[flip]) / (float)C + eps);
+      flip ^= 1;
     }
 #pragma unroll
     for (int i = 0; i < CHUNKS; ++i) {
-      const int ch = threadIdx.x + i * THREADS;
+      const int ch = threadIdx.x + i * kRowThreads;
       if (ch < nchunks) {
         const int c0 = ch * 8;
         float v[8], y[8];
@@ -339,11 +337,10 @@ __global__ void cfg_euler_kernel(__nv_bfloat16* __restrict__ lat, const __nv_bfl
 }
 
 int g_row_ctas_per_sm = 0;   // 0 = as many as fit (occupancy query per kernel); n > 0 forces n (fwb_rowwise_set_ctas_per_sm, A/B only)
-int g_row_wide_threads = 128;   // CTA width for rows of more than 2048 elements: 128 (5 chunks per thread) or 256 (3), fwb_rowwise_set_threads
 
 // Grid of a persistent row kernel: (resident CTAs per SM) x #SMs — exactly one wave, so no CTA waits for a slot and the rows are dealt
 // evenly (measured: a grid of 8 CTAs/SM when only 6 fit costs +27 %) — and never more than one CTA per row.
-template <auto Kernel, int THREADS>
+template <auto Kernel>
 inline int row_grid(int rows) {
   static int occ[64] = {0};                       // per kernel instantiation and device ordinal
   int per_sm = g_row_ctas_per_sm;
@@ -353,7 +350,7 @@ inline int row_grid(int rows) {
     if (slot && *slot > 0) {
       per_sm = *slot;
     } else {
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, Kernel, THREADS, 0) != cudaSuccess || per_sm <= 0) per_sm = 4;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, Kernel, kRowThreads, 0) != cudaSuccess || per_sm <= 0) per_sm = 4;
       if (slot) *slot = per_sm;
     }
   }
@@ -369,12 +366,6 @@ extern "C" int fwb_rowwise_set_ctas_per_sm(int n) {
   return FWB_OK;
 }
 
-extern "C" int fwb_rowwise_set_threads(int n) {
-  FWB_CHECK(n == 128 || n == 256, "rowwise_set_threads: 128 or 256 threads per CTA for rows of more than 2048 elements");
-  g_row_wide_threads = n;
-  return FWB_OK;
-}
-
 extern "C" int fwb_ln_modulate(const void* x, int x_dtype, int64_t ldx, int rows, int C, float eps, const float* w,
                                const float* b, const float* mul, const float* add, void* out, int64_t ldo,
                                cudaStream_t stream) {
@@ -386,20 +377,19 @@ extern "C" int fwb_ln_modulate(const void* x, int x_dtype, int64_t ldx, int rows
   const int chunks = (C / 8 + kRowThreads - 1) / kRowThreads;
   const bool f32 = x_dtype == FWB_DT_F32;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-#define LAUNCH_K(TH, CH, F32)                                                                                                   \
-  ln_modulate_kernel<TH, CH, F32><<<row_grid<ln_modulate_kernel<TH, CH, F32>, TH>(rows), TH, 0, stream>>>(x, ldx, rows, C, eps, w, \
-                                                                                                         b, mul, add, o, ldo)
-#define LAUNCH(TH, CH)                    \
-  do {                                    \
-    if (f32) LAUNCH_K(TH, CH, true);      \
-    else LAUNCH_K(TH, CH, false);         \
+#define LAUNCH(CH)                                                                                                \
+  do {                                                                                                            \
+    if (f32)                                                                                                      \
+      ln_modulate_kernel<CH, true><<<row_grid<ln_modulate_kernel<CH, true>>(rows), kRowThreads, 0, stream>>>(     \
+          x, ldx, rows, C, eps, w, b, mul, add, o, ldo);                                                          \
+    else                                                                                                          \
+      ln_modulate_kernel<CH, false><<<row_grid<ln_modulate_kernel<CH, false>>(rows), kRowThreads, 0, stream>>>(   \
+          x, ldx, rows, C, eps, w, b, mul, add, o, ldo);                                                          \
   } while (0)
-  if (chunks <= 1) LAUNCH(128, 1);
-  else if (chunks <= 2) LAUNCH(128, 2);
-  else if (g_row_wide_threads == 256) LAUNCH(256, 3);
-  else LAUNCH(128, 5);
+  if (chunks <= 1) LAUNCH(1);
+  else if (chunks <= 2) LAUNCH(2);
+  else LAUNCH(5);
 #undef LAUNCH
-#undef LAUNCH_K
   FWB_CUDA(cudaGetLastError());
   return FWB_OK;
 }
@@ -413,14 +403,9 @@ extern "C" int fwb_rmsnorm_rope(void* x, int64_t ldx, int rows, int C, const flo
   const int chunks = (C / 8 + kRowThreads - 1) / kRowThreads;
   __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(x);
   const float2* cs = reinterpret_cast<const float2*>(cos_sin);
-#define LAUNCH(TH, CH)                                                                                                        \
-  rmsnorm_rope_kernel<TH, CH><<<row_grid<rmsnorm_rope_kernel<TH, CH>, TH>(rows), TH, 0, stream>>>(xp, ldx, rows, C, w, eps, cs, \
-                                                                                                  head_dim)
-  if (chunks <= 1) LAUNCH(128, 1);
-  else if (chunks <= 2) LAUNCH(128, 2);
-  else if (g_row_wide_threads == 256) LAUNCH(256, 3);
-  else LAUNCH(128, 5);
-#undef LAUNCH
+  if (chunks <= 1) rmsnorm_rope_kernel<1><<<row_grid<rmsnorm_rope_kernel<1>>(rows), kRowThreads, 0, stream>>>(xp, ldx, rows, C, w, eps, cs, head_dim);
+  else if (chunks <= 2) rmsnorm_rope_kernel<2><<<row_grid<rmsnorm_rope_kernel<2>>(rows), kRowThreads, 0, stream>>>(xp, ldx, rows, C, w, eps, cs, head_dim);
+  else rmsnorm_rope_kernel<5><<<row_grid<rmsnorm_rope_kernel<5>>(rows), kRowThreads, 0, stream>>>(xp, ldx, rows, C, w, eps, cs, head_dim);
   FWB_CUDA(cudaGetLastError());
   return FWB_OK;
 }

@@ -63,7 +63,6 @@ def _load():
     lib.fwb_bringup_mma.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
     lib.fwb_bringup_mma_pv_n.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.fwb_rowwise_set_ctas_per_sm.argtypes = [i32]
-    lib.fwb_rowwise_set_threads.argtypes = [i32]
     lib.fwb_ln_modulate.argtypes = [vp, i32, i64, i32, i32, f32, vp, vp, vp, vp, vp, i64, vp]
     lib.fwb_rmsnorm_rope.argtypes = [vp, i64, i32, i32, vp, f32, vp, i32, vp]
     lib.fwb_ln64_rope2d.argtypes = [vp, i64, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp]

@@ -149,9 +149,6 @@ int fwb_ln_modulate(const void* x, int x_dtype, int64_t ldx, int rows, int C, fl
 /* Tuning hook: 128-thread CTAs per SM of the persistent row kernels (fwb_ln_modulate, fwb_rmsnorm_rope): 0 = one full wave of as many
  * as fit (occupancy query per kernel, default), 1..16 = forced (A/B measurements) */
 int fwb_rowwise_set_ctas_per_sm(int n);
-/* Tuning hook: threads per CTA of the row kernels on rows of more than 2048 elements: 128 (five 8-element chunks per thread) or 256
- * (three).  The element-to-thread mapping, hence the fp32 summation order of the row statistics, differs between the two. */
-int fwb_rowwise_set_threads(int n);
 
 /* ---- K8+K9 (DiT / adapter): full-channel RMSNorm then interleaved-pair RoPE, in place --------------------------------
  * x[r,:] <- rope( bf16( bf16(x * rsqrt(mean(x^2)+eps)) * w ) ), w == NULL skips the norm, cos_sin == NULL skips RoPE.

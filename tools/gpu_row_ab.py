@@ -1,4 +1,4 @@
-"""A/B of the persistent row kernels on the GPU: 128- vs 256-thread CTAs on wide rows (fwb_rowwise_set_threads), and CTAs per SM.
+"""Timing of the persistent row kernels on the GPU at the in-step shapes, by CTAs per SM (fwb_rowwise_set_ctas_per_sm; 0 = automatic).
 CUDA-event times over many launches at the in-step shapes; inputs (671 MB .. 1 GB per launch) exceed the 126 MB L2.
 
     python tools/gpu_row_ab.py            # prints TB/s per configuration (algorithmic bytes: read + write once)
@@ -42,14 +42,11 @@ def main():
     ]
     for name, fn, nbytes in cases:
         line = [f"{name:40s}"]
-        for threads in (128, 256):
-            for ctas in (0, 2, 3, 4):
-                fwb200.lib.fwb_rowwise_set_threads(threads)
-                fwb200.lib.fwb_rowwise_set_ctas_per_sm(ctas)
-                t = timeit(fn)
-                line.append(f"t{threads}/cta{ctas}: {nbytes / t / 1e12:5.2f}")
+        for ctas in (0, 2, 3, 4, 6, 8):
+            fwb200.lib.fwb_rowwise_set_ctas_per_sm(ctas)
+            t = timeit(fn)
+            line.append(f"cta{ctas}: {nbytes / t / 1e12:5.2f}")
         print(" | ".join(line), flush=True)
-    fwb200.lib.fwb_rowwise_set_threads(128)
     fwb200.lib.fwb_rowwise_set_ctas_per_sm(0)
 
 
