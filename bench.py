@@ -324,7 +324,7 @@ def roofline_from_prof(prof, L, world, step_ms_total, sustained_peak, peak_src, 
             traffic_src = rec.get("source", "ncu --set full capture, see profiles/")
         except Exception:
             traffic = None
-    return {"kernel": kernel or "attn_fwd_kernel<128> (DiT self-attention, fwb_attn_fwd / fwb_attn_fwd_partial)", "bound": "tensor",
+    return {"kernel": kernel or "attn_fwd_mc_kernel<128> (DiT self-attention: aliased S/P kernel in K/V-multicast CTA pairs, fwb_attn_fwd / fwb_attn_fwd_partial)", "bound": "tensor",
             "achieved": ach, "peak": sustained_peak, "unit": "TFLOP/s", "frac": ach / sustained_peak, "traffic": traffic,
             "traffic_source": traffic_src,
             "launches_timed": cnt, "ms_per_launch": tot / cnt, "flop_per_launch": fl_total / cnt,
