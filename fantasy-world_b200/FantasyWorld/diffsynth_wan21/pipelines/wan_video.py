@@ -65,15 +65,40 @@ class WanVideoPipeline(nn.Module):
         self.vae = self._attach(WanVideoVAE(z_dim=z_dim), state_dict, device, dtype)
         return self.vae
 
+    def _materialize(self, model, state_dict, device, dtype, init):
+        """A model built under torch.device("meta") gets its storage directly on the target device (umT5-XXL is 5.7 B parameters:
+        never on the host in fp32): from `state_dict` when given, else random-initialised there by `init(model)`."""
+        from fwb_synth import materialize
+        device, dtype = device or self.device, dtype or self.torch_dtype
+        if state_dict is not None:
+            model.load_state_dict(state_dict, strict=True, assign=True)
+            return model.to(device=device, dtype=dtype).eval()
+        materialize(model, device, dtype)
+        with torch.no_grad():
+            init(model)
+        return model.eval()
+
     def enable_text_encoder(self, state_dict=None, device=None, dtype=None, **config):
-        from ..models.wan_video_text_encoder import WanTextEncoder
-        self.text_encoder = self._attach(WanTextEncoder(**config), state_dict, device, dtype)
+        """Attach the umT5 encoder mirror: `state_dict` in the released checkpoint's layout, else the encoder's own random init."""
+        from ..models.wan_video_text_encoder import WanTextEncoder, init_weights
+
+        def init(m):
+            m.apply(init_weights)
+            nn.init.normal_(m.token_embedding.weight)
+
+        with torch.device("meta"):
+            model = WanTextEncoder(**config)
+        self.text_encoder = self._materialize(model, state_dict, device, dtype, init)
         self.prompter.fetch_models(self.text_encoder)
         return self.text_encoder
 
-    def enable_image_encoder(self, state_dict=None, device=None, dtype=None, **config):
+    def enable_image_encoder(self, state_dict=None, device=None, dtype=None, seed=0, **config):
+        """Attach the CLIP image tower mirror: `state_dict` with the `model.*` keys (after the converter), else per-key synthetic
+        weights (fwb_synth) generated on the device."""
+        from fwb_synth import synth_init
         from ..models.wan_video_image_encoder import WanImageEncoder
-        self.image_encoder = self._attach(WanImageEncoder(**config), state_dict, device, dtype)
+        model = WanImageEncoder(device="meta", **config)
+        self.image_encoder = self._materialize(model, state_dict, device, dtype, lambda m: synth_init(m, seed))
         return self.image_encoder
 
     # -- sampler helpers -----------------------------------------------------------------------------------------------------
