@@ -15,65 +15,64 @@ import torch
 
 from .base_prompter import BasePrompter
 
+_WS = re.compile(r"\s+")
+_NO_PUNCT = str.maketrans("", "", string.punctuation)
+
 
 def basic_clean(text):
     import ftfy          # same dependency as the reference (wan_prompter.py:5,12): mojibake repair has no stand-in
-    text = ftfy.fix_text(text)
-    return html.unescape(html.unescape(text)).strip()
+    return html.unescape(html.unescape(ftfy.fix_text(text))).strip()
 
 
 def whitespace_clean(text):
-    return re.sub(r"\s+", " ", text).strip()
+    return _WS.sub(" ", text).strip()
 
 
 def canonicalize(text, keep_punctuation_exact_string=None):
     """Underscores to spaces, punctuation stripped (except an exact marker string), lower-cased, whitespace collapsed."""
-    strip = str.maketrans("", "", string.punctuation)
     text = text.replace("_", " ")
-    if keep_punctuation_exact_string:
-        text = keep_punctuation_exact_string.join(part.translate(strip) for part in text.split(keep_punctuation_exact_string))
-    else:
-        text = text.translate(strip)
-    return re.sub(r"\s+", " ", text.lower()).strip()
+    pieces = text.split(keep_punctuation_exact_string) if keep_punctuation_exact_string else [text]
+    text = (keep_punctuation_exact_string or "").join(piece.translate(_NO_PUNCT) for piece in pieces)
+    return whitespace_clean(text.lower())
+
+
+_CLEANERS = {
+    None: lambda t: t,
+    "whitespace": lambda t: whitespace_clean(basic_clean(t)),
+    "lower": lambda t: whitespace_clean(basic_clean(t)).lower(),
+    "canonicalize": lambda t: canonicalize(basic_clean(t)),
+}
 
 
 class HuggingfaceTokenizer:
+    """`AutoTokenizer` with a cleaning mode and (optionally) fixed-length padding / truncation (wan_prompter.py:36-80)."""
+
     def __init__(self, name, seq_len=None, clean=None, **kwargs):
-        assert clean in (None, "whitespace", "lower", "canonicalize")
-        self.name, self.seq_len, self.clean = name, seq_len, clean
+        if clean not in _CLEANERS:
+            raise AssertionError(f"clean must be one of {list(_CLEANERS)}")
         from transformers import AutoTokenizer
+        self.name, self.seq_len, self.clean = name, seq_len, clean
         self.tokenizer = AutoTokenizer.from_pretrained(name, **kwargs)
         self.vocab_size = self.tokenizer.vocab_size
 
-    def __call__(self, sequence, **kwargs):
-        return_mask = kwargs.pop("return_mask", False)
-        call = {"return_tensors": "pt"}
-        if self.seq_len is not None:
-            call.update(padding="max_length", truncation=True, max_length=self.seq_len)
-        call.update(**kwargs)
-        if isinstance(sequence, str):
-            sequence = [sequence]
-        if self.clean:
-            sequence = [self._clean(u) for u in sequence]
-        enc = self.tokenizer(sequence, **call)
-        return (enc.input_ids, enc.attention_mask) if return_mask else enc.input_ids
-
     def _clean(self, text):
-        if self.clean == "whitespace":
-            return whitespace_clean(basic_clean(text))
-        if self.clean == "lower":
-            return whitespace_clean(basic_clean(text)).lower()
-        if self.clean == "canonicalize":
-            return canonicalize(basic_clean(text))
-        return text
+        return _CLEANERS[self.clean](text)
+
+    def __call__(self, sequence, **kwargs):
+        want_mask = kwargs.pop("return_mask", False)
+        texts = [sequence] if isinstance(sequence, str) else list(sequence)
+        options = dict(return_tensors="pt")
+        if self.seq_len is not None:
+            options.update(padding="max_length", truncation=True, max_length=self.seq_len)
+        options.update(kwargs)
+        enc = self.tokenizer([self._clean(t) for t in texts], **options)
+        return (enc.input_ids, enc.attention_mask) if want_mask else enc.input_ids
 
 
 class WanPrompter(BasePrompter):
     def __init__(self, tokenizer_path=None, text_len=512):
         super().__init__()
-        self.text_len = text_len
-        self.text_encoder = None
-        self.tokenizer = None
+        self.text_len, self.text_encoder, self.tokenizer = text_len, None, None
         self.fetch_tokenizer(tokenizer_path)
 
     def fetch_tokenizer(self, tokenizer_path=None):
@@ -87,11 +86,11 @@ class WanPrompter(BasePrompter):
     def encode_prompt(self, prompt, positive=True, device="cuda"):
         if self.tokenizer is None or self.text_encoder is None:
             raise RuntimeError("WanPrompter.encode_prompt: fetch_tokenizer(path) and fetch_models(text_encoder) first")
-        prompt = self.process_prompt(prompt, positive=positive)
-        ids, mask = self.tokenizer(prompt, return_mask=True, add_special_tokens=True)
-        ids, mask = ids.to(device), mask.to(device)
-        emb = self.text_encoder(ids, mask)
+        ids, mask = self.tokenizer(self.process_prompt(prompt, positive=positive), return_mask=True, add_special_tokens=True)
+        mask = mask.to(device)
+        emb = self.text_encoder(ids.to(device), mask)
         # the reference zeroes [:, v:] for EVERY sequence's length v in turn (wan_prompter.py:106-108), i.e. from the shortest
         # length on, for the whole batch; with the single prompt the sampler passes this is "zero the padding"
-        emb[:, int(mask.gt(0).sum(dim=1).min()):] = 0
+        shortest = int((mask > 0).sum(dim=1).min())
+        emb[:, shortest:] = 0
         return emb
