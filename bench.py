@@ -544,7 +544,9 @@ def run_ours(args):
                        "l2": "per-step working set (37 GB weights + >1 GB activations) exceeds the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_sps, "unit": "steps/s", "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                     "api": ("denoise_step_experts" if wan22 else "FantasyWorldFusionModel.denoise_step") +
-                           " from pinned host latents; conditioning uploaded once per run inside the timed region"},
+                           " from pinned host latents; conditioning uploaded once per run inside the timed region",
+                    "note": "its own timed region of the same K steps, run after `value`'s; the copies (41 MB in, 4 MB out per step) are "
+                            "0.01 % of a step, so the two differ by the board's run-to-run spread under its power cap (about +-1.5 %)"},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
             "gpu_reference": gpu_ref}
     if args.breakdown:
