@@ -41,9 +41,11 @@ def _build_side_model(name):
 
 
 class ModelManager:
-    def __init__(self, torch_dtype=torch.bfloat16, device="cpu", dit_config: dict | None = None):
+    def __init__(self, torch_dtype=torch.bfloat16, device="cpu", dit_config: dict | None = None, side_configs: dict | None = None):
+        """`side_configs` (extension, tests): constructor overrides per side model name, e.g. {"wan_video_text_encoder": {...}}."""
         self.torch_dtype, self.device = torch_dtype, device
         self.dit_config = dict(dit_config or WAN21_I2V_14B)
+        self.side_configs = dict(side_configs or {})
         self.models = {}
         self.model_paths = {}
 
@@ -53,13 +55,14 @@ class ModelManager:
         if name is None:
             return None
         cls = _build_side_model(name)
+        cfg = self.side_configs.get(name, {})
         if name == "wan_video_vae":
-            model = cls()                        # small; holds plain (non-parameter) mean / std tensors
+            model = cls(**cfg)                   # small; holds plain (non-parameter) mean / std tensors
         elif name == "wan_video_image_encoder":
-            model = cls(device="meta")
+            model = cls(device="meta", **cfg)
         else:
             with torch.device("meta"):
-                model = cls()
+                model = cls(**cfg)
         sd = cls.state_dict_converter().from_civitai(state_dict)
         model.load_state_dict(sd, strict=True, assign=True)
         model = model.to(device=device or self.device, dtype=torch_dtype or self.torch_dtype).eval()

@@ -146,6 +146,37 @@ def test_model_manager_detects_side_checkpoints():
     assert mm.fetch_model("wan_video_text_encoder", require_model_path=True) is None
 
 
+def test_pipeline_fetches_side_models_from_checkpoints(tmp_path):
+    """inference_wan21.py:183-188 hands the DiT shards plus three `.pth` files to the model manager; the pipeline must come back with the
+    text encoder, the image encoder and the VAE attached (their keys are part of the fusion model's state_dict: `pipe.text_encoder.*`
+    ... — the CLI asserts that the released checkpoint has no unexpected keys).  Reduced towers, files in the released layouts."""
+    from FantasyWorld.diffsynth_wan21.models.model_manager import ModelManager
+    from FantasyWorld.diffsynth_wan21.models.wan_video_vae import WanVideoVAE
+    from FantasyWorld.diffsynth_wan21.pipelines.wan_video import WanVideoPipeline
+    g = gold("encoders.pt")
+    t5, clip, vae = _t5(g["t5_cfg"]), _clip(g["clip_cfg"]), WanVideoVAE(z_dim=16)
+    t5_path, clip_path, vae_path = (tmp_path / n for n in ("models_t5_umt5-xxl-enc-bf16.pth", "models_clip.pth", "Wan2.1_VAE.pth"))
+    torch.save(t5.state_dict(), t5_path)
+    clip_sd = {k[len("model."):]: v for k, v in clip.state_dict().items()}
+    clip_sd["textual.token_embedding.weight"] = torch.zeros(4, 4)                  # the released file also holds the text tower
+    torch.save(clip_sd, clip_path)
+    torch.save({k[len("model."):]: v for k, v in vae.state_dict().items()}, vae_path)
+    mm = ModelManager(torch_dtype=BF16, device="cpu", dit_config=dict(dim=64, in_dim=36, ffn_dim=128, out_dim=16, text_dim=64, freq_dim=32,
+                                                                        eps=1e-6, patch_size=(1, 2, 2), num_heads=2, num_layers=1,
+                                                                        has_image_input=True),
+                      side_configs={"wan_video_text_encoder": g["t5_cfg"], "wan_video_image_encoder": g["clip_cfg"]})
+    mm.load_models([[], str(vae_path), str(clip_path), str(t5_path)])
+    pipe = WanVideoPipeline.from_model_manager(mm, device="cpu")
+    assert pipe.dit is not None and pipe.vae is not None and pipe.image_encoder is not None and pipe.text_encoder is not None
+    assert pipe.prompter.text_encoder is pipe.text_encoder and pipe.prompter.tokenizer is None      # no google/umt5-xxl dir next to the file
+    for ours, src in ((pipe.text_encoder, t5), (pipe.image_encoder, clip)):
+        a, b = ours.state_dict(), src.state_dict()
+        assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    keys = {k for k, _ in pipe.named_parameters()}
+    assert "text_encoder.blocks.0.attn.q.weight" in keys and "image_encoder.model.visual.pre_norm.weight" in keys
+    assert any(k.startswith("vae.model.") for k in keys)
+
+
 def test_encoders_refuse_to_run_without_the_device():
     """No CPU fallback: without a B200 the mirrors raise instead of computing something else."""
     if torch.cuda.is_available():
