@@ -17,7 +17,7 @@ Convolutions / interpolation stay on cuDNN / ATen (once per video; the hand-writ
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import torch
 import torch.nn as nn

@@ -6,8 +6,6 @@ control-adapter added in patchify); everything after that is identical and lives
 """
 from __future__ import annotations
 
-from typing import Optional
-
 import torch
 import torch.nn as nn
 

@@ -11,7 +11,6 @@ Results are the same tensors the reference computes, at the reference's own roun
 """
 from __future__ import annotations
 
-import copy
 from typing import Optional
 
 import torch
