@@ -225,6 +225,7 @@ class WanVideoVAE(nn.Module):
         self.scale = [self.mean, 1.0 / self.std]
         self.model = VideoVAE_(z_dim=z_dim).eval().requires_grad_(False)
         self.upsampling_factor = 8
+        self.z_dim = z_dim
 
     # ---- blending masks (ref: :621-641) --------------------------------------------------------------------------------------
     @staticmethod
@@ -293,11 +294,38 @@ class WanVideoVAE(nn.Module):
     def single_encode(self, video, device):
         return self.model.encode(video.to(device), self.scale)
 
+    def tiled_encode(self, video, device, tile_size, tile_stride):
+        """The encoder on overlapping PIXEL tiles (sizes in pixels), blended on the latent grid with the same linear ramps as the tiled
+        decode (ref: :695-743; used by the Wan2.2 conditioning call, inference_wan22.py:345-351 with tiled=True).  Accumulates on
+        `device` (the reference accumulates on the CPU: same additions in the same order)."""
+        _, _, T, H, W = video.shape
+        f = self.upsampling_factor
+        dt = video.dtype
+        out_T = (T + 3) // 4
+        z = self.model.z_dim
+        weight = torch.zeros((1, 1, out_T, H // f, W // f), dtype=dt, device=device)
+        values = torch.zeros((1, z, out_T, H // f, W // f), dtype=dt, device=device)
+        border = ((tile_size[0] - tile_stride[0]) // f, (tile_size[1] - tile_stride[1]) // f)
+        for h0, h1, w0, w1 in self.tile_tasks(H, W, tile_size, tile_stride):
+            tile = self.model.encode(video[:, :, :, h0:h1, w0:w1].to(device), self.scale)
+            mask = self.build_mask(tile, is_bound=(h0 == 0, h1 >= H, w0 == 0, w1 >= W), border_width=border).to(dtype=dt, device=device)
+            th, tw = h0 // f, w0 // f
+            values[:, :, :, th:th + tile.shape[3], tw:tw + tile.shape[4]] += tile * mask
+            weight[:, :, :, th:th + tile.shape[3], tw:tw + tile.shape[4]] += mask
+        return values / weight
+
     def encode(self, videos: Sequence[torch.Tensor], device, tiled=False, tile_size=(34, 34), tile_stride=(18, 16)):
-        """videos: iterable of [3, T, H, W] -> [n, 16, 1 + (T-1)/4, H/8, W/8] (untiled; tiled encoding is not mirrored).  ref: :758-774."""
-        if tiled:
-            raise NotImplementedError("tiled VAE encoding is not part of this build (first-frame conditioning uses the untiled path)")
-        return torch.stack([self.single_encode(v.unsqueeze(0), device).squeeze(0) for v in videos])
+        """videos: iterable of [3, T, H, W] -> [n, 16, 1 + (T-1)/4, H/8, W/8]; `tile_size` / `tile_stride` in latent cells.  ref: :758-774."""
+        f = self.upsampling_factor
+        out = []
+        for v in videos:
+            v = v.unsqueeze(0)
+            if tiled:
+                z = self.tiled_encode(v, device, (tile_size[0] * f, tile_size[1] * f), (tile_stride[0] * f, tile_stride[1] * f))
+            else:
+                z = self.single_encode(v, device)
+            out.append(z.squeeze(0))
+        return torch.stack(out)
 
     def decode(self, hidden_states, device, tiled=False, tile_size=(34, 34), tile_stride=(18, 16), group=None):
         """ref: :776-783 (call site inference_wan21.py:324-330)."""

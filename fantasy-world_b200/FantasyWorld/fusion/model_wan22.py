@@ -85,9 +85,14 @@ class FantasyWorldFusionModel(FusionCore):
                  load_text_encoder=False, dit_config: dict | None = None):
         super().__init__()
         self.device = "cuda"
-        pipe = WanVideoPipeline.from_pretrained(
-            torch_dtype=torch.bfloat16, device="cpu", tokenizer_config=None, dit_config=dit_config,
-            model_configs=[ModelConfig(model_id=model_id, origin_file_pattern=origin_file_pattern, local_model_path=dit_path)])
+        configs = [ModelConfig(model_id=model_id, origin_file_pattern=origin_file_pattern, local_model_path=dit_path)]
+        extra = dict(tokenizer_config=None)
+        if load_vae and load_text_encoder:       # the expert that also serves the conditioning call and the final decode (ref: :144-163)
+            configs += [ModelConfig(model_id=model_id, origin_file_pattern="models_t5_umt5-xxl-enc-bf16.pth", local_model_path=dit_path),
+                        ModelConfig(model_id=model_id, origin_file_pattern="Wan2.1_VAE.pth", local_model_path=dit_path)]
+            extra = {}                             # default tokenizer_config: the google/umt5-xxl directory
+        pipe = WanVideoPipeline.from_pretrained(torch_dtype=torch.bfloat16, device="cpu", dit_config=dit_config, model_configs=configs,
+                                                **extra)
         pipe.device = "cpu"
         load_lora(pipe, lora_path, 0.55, "dit")
         self.pipe = pipe
