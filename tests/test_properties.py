@@ -7,7 +7,7 @@ import torch
 from hypothesis import given, settings, strategies as st
 
 
-@settings(max_examples=300, deadline=None)
+@settings(max_examples=300, deadline=None, derandomize=True)
 @given(B=st.integers(1, 24), H=st.integers(1, 48), Lq=st.integers(1, 40000), Lk=st.integers(1, 40000), D=st.sampled_from([64, 96, 128]),
        sms=st.sampled_from([74, 132, 148, 160]), ws_mb=st.sampled_from([0, 1, 16, 78, 512]))
 def test_attention_plan_invariants(B, H, Lq, Lk, D, sms, ws_mb):
@@ -30,7 +30,7 @@ def test_attention_plan_invariants(B, H, Lq, Lk, D, sms, ws_mb):
         assert split_cost <= 0.93 * (waves + 1) + 1e-9
 
 
-@settings(max_examples=200, deadline=None)
+@settings(max_examples=200, deadline=None, derandomize=True)
 @given(H=st.integers(1, 70), W=st.integers(1, 110), sh=st.integers(1, 40), sw=st.integers(1, 60), dh=st.integers(1, 40), dw=st.integers(1, 60))
 def test_vae_tiles_cover_the_grid_with_positive_weight(H, W, sh, sw, dh, dw):
     """Every latent cell is covered by at least one tile and the accumulated blending weight is positive everywhere (no 0 / 0 in
@@ -51,7 +51,7 @@ def test_vae_tiles_cover_the_grid_with_positive_weight(H, W, sh, sw, dh, dw):
     assert tasks[0][0] == 0 and tasks[0][2] == 0 and len(set(tasks)) == len(tasks)
 
 
-@settings(max_examples=200, deadline=None)
+@settings(max_examples=200, deadline=None, derandomize=True)
 @given(h=st.integers(1, 2000), w=st.integers(1, 2000), f=st.integers(1, 400))
 def test_wan22_shape_rounding(h, w, f):
     from FantasyWorld.diffsynth_wan22.pipelines.wan_video_new import WanVideoPipeline
