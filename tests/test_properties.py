@@ -59,3 +59,20 @@ def test_wan22_shape_rounding(h, w, f):
     H, W, F = pipe.check_resize_height_width(h, w, f)
     assert H % 16 == 0 and W % 16 == 0 and F % 4 == 1 and 0 <= H - h < 16 and 0 <= W - w < 16 and 0 <= F - f <= 4
     assert pipe.check_resize_height_width(H, W, F) == (H, W, F)          # idempotent
+
+
+@settings(max_examples=200, deadline=None, derandomize=True)
+@given(world=st.integers(1, 8), f=st.integers(1, 40), h=st.integers(1, 48), w=st.integers(1, 80))
+def test_sequence_parallel_layout_partitions_both_streams(world, f, h, w):
+    """Video rows: contiguous shards differing by at most one row; geometry rows: whole frames per rank (frame attention needs no
+    exchange), differing by at most one frame; both cover their stream exactly once, in rank order."""
+    from fwb200.sp import SPLayout
+    lay = SPLayout(world=world, f=f, h=h, w=w)
+    for ranges, total, sizes in ((([lay.video_range(r) for r in range(world)]), lay.L, lay.video_rows),
+                                (([lay.geo_range(r) for r in range(world)]), lay.N, lay.geo_rows())):
+        assert ranges[0][0] == 0 and ranges[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        assert [b - a for a, b in ranges] == list(sizes) and sum(sizes) == total
+    assert max(lay.video_rows) - min(lay.video_rows) <= 1 and max(lay.frames) - min(lay.frames) <= 1
+    assert all(r % lay.P == 0 for r in lay.geo_rows()) and lay.P == 5 + h * w
+    assert sorted(lay.video_rows, reverse=True) == lay.video_rows          # the larger shards come first
