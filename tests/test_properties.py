@@ -76,3 +76,23 @@ def test_sequence_parallel_layout_partitions_both_streams(world, f, h, w):
     assert max(lay.video_rows) - min(lay.video_rows) <= 1 and max(lay.frames) - min(lay.frames) <= 1
     assert all(r % lay.P == 0 for r in lay.geo_rows()) and lay.P == 5 + h * w
     assert sorted(lay.video_rows, reverse=True) == lay.video_rows          # the larger shards come first
+
+
+@settings(max_examples=100, deadline=None, derandomize=True)
+@given(n=st.integers(1, 200), shift=st.floats(1.0, 12.0), extra=st.booleans())
+def test_flow_match_schedule_properties(n, shift, extra):
+    """Sigmas start at 1 (shift maps 1 -> 1), decrease strictly, every Euler increment is negative and the increments telescope to
+    -sigma_0 (the sampler integrates the whole way to sigma = 0); a constant velocity field is integrated exactly."""
+    from FantasyWorld.diffsynth_wan21.schedulers.flow_match import FlowMatchScheduler
+    s = FlowMatchScheduler(shift=shift, sigma_min=0.0, extra_one_step=extra)
+    s.set_timesteps(n)
+    sig = s.sigmas
+    assert len(sig) == n and abs(float(sig[0]) - 1.0) < 1e-6 and bool((sig[1:] < sig[:-1]).all()) and float(sig[-1]) >= 0.0
+    assert torch.equal(s.timesteps, sig * 1000)
+    steps = [s.dsigma(t) for t in s.timesteps]
+    assert all(d < 0 for d in steps[:-1]) and steps[-1] <= 0
+    assert abs(sum(steps) + float(sig[0])) < 1e-4
+    x = torch.zeros(3)
+    for t in s.timesteps:
+        x = s.step(torch.ones(3), t, x)
+    assert torch.allclose(x, torch.full((3,), -float(sig[0])), atol=1e-4)
