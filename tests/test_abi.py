@@ -108,3 +108,34 @@ def test_attention_tile_schedule_planner():
     # no workspace -> no split; tile count a multiple of the SM count -> no split
     assert plan(1, 40, 4095, 8190, 128, ws_bytes=0)[2] == 1
     assert plan(1, 37, 1024, 8192, 128)[2] == 1           # 4 * 37 = 148 tiles
+
+
+def test_product_never_imports_test_infrastructure():
+    """Contract: oracle/ (the CPU restatement + the staged reference) and tests/ are checkers.  Nothing under fantasy-world_b200/ may import
+    them, and outside tests/ only __graft_entry__.smoke()/build(), bench.py (its CPU legs) and the golden / debug tools under tools/ do."""
+    import ast
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    banned = ("oracle", "tests", "_ops_torch_shim", "_common", "ref_shim", "make_ref", "ref_runner", "fw_oracle")
+
+    def imported_roots(path):
+        out = set()
+        for node in ast.walk(ast.parse(path.read_text())):
+            if isinstance(node, ast.Import):
+                out |= {a.name.split(".")[0] for a in node.names}
+            elif isinstance(node, ast.ImportFrom) and node.module and node.level == 0:
+                out.add(node.module.split(".")[0])
+                out |= {a.name for a in node.names if node.module.split(".")[0] in banned}
+        return out
+
+    offenders = []
+    for f in (root / "fantasy-world_b200").rglob("*.py"):
+        if "build" in f.parts[len(root.parts):][1:2]:
+            continue
+        hit = imported_roots(f) & set(banned)
+        if hit:
+            offenders.append((str(f.relative_to(root)), sorted(hit)))
+    assert not offenders, offenders
+    # the C sources do not reference the oracle either (no CPU fallback is linked in)
+    for f in (root / "fantasy-world_b200" / "csrc").glob("*"):
+        assert "oracle" not in f.read_text().lower(), f
