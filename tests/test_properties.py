@@ -96,3 +96,20 @@ def test_flow_match_schedule_properties(n, shift, extra):
     for t in s.timesteps:
         x = s.step(torch.ones(3), t, x)
     assert torch.allclose(x, torch.full((3,), -float(sig[0])), atol=1e-4)
+
+
+def test_bench_flop_accounting_matches_baseline_table():
+    """bench.forward_flops is the denominator of every throughput / roofline figure.  It must agree with BASELINE.md §2 (2.134 PFLOP per C2
+    forward, 8.548 per C4 forward, 0.758 at the Wan2.1 CLI default, 21.70 for the 81-latent-frame stress row) and never exceed it: the
+    bench leaves out what the engine hoists out of the loop (context K/V projections, camera group-1 MLP, embeddings), which is at most
+    1 % of a forward, so the reported TFLOP/s can only be conservative.  Per-call attention figures: 21.98 / 9.92 / 4.42 TFLOP."""
+    import bench
+    rows = (((21, 30, 52, 16, 24), {}, 2.134), ((21, 45, 80, 16, 24), dict(clip=False, camera_adaln=False), 8.548),
+            ((21, 21, 37, 16, 24), {}, 0.758), ((81, 30, 52, 16, 24), {}, 21.70))
+    for args, kw, ref in rows:
+        ours = bench.forward_flops(*args, **kw) / 1e15
+        assert 0.988 * ref <= ours <= 1.0005 * ref, (args, ours, ref)
+    L, N = 21 * 30 * 52, 21 * (5 + 30 * 52)
+    assert round(4 * 40 * L * L * 128 / 1e12, 2) == 21.98 and round(2 * 4 * 12 * L * N * 96 / 1e12, 2) == 9.92
+    assert round(4 * 16 * N * N * 64 / 1e12, 2) == 4.42
+    assert bench.forward_flops(21, 30, 52, 16, 24) < bench.forward_flops(22, 30, 52, 16, 24) < bench.forward_flops(22, 31, 52, 16, 25)
