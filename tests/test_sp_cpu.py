@@ -1,4 +1,4 @@
-"""Sequence-parallel host logic on CPU: world_size-2 (and 3) gloo process groups.  Checks the shard layout (video rows,
+"""Sequence-parallel host logic on CPU: world_size 2, 3 and 8 gloo process groups.  Checks the shard layout (video rows,
 frame-aligned geometry rows), the packed all-gather (equal and ragged shards) and that "local queries x gathered keys"
 reproduces the rows of the un-sharded attention (oracle math) — the only cross-rank dependency of the hot path."""
 import os
@@ -55,7 +55,7 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 8])
 def test_sp_layout_and_gather_gloo(world):
     port = _free_port()
     mgr = mp.Manager()
@@ -99,7 +99,7 @@ def _cfg_worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_cfg_parallel_groups_and_exchange_gloo(world):
     port = _free_port()
     mgr = mp.Manager()
